@@ -1,0 +1,617 @@
+// C-ABI entry points of libb200rag.so (include/b200rag.h) and the host-side orchestration of one shard.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace b200rag {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    if (e == cudaErrorMemoryAllocation) return B200RAG_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return B200RAG_ERR_NOGPU;
+    return B200RAG_ERR_CUDA;
+}
+
+int DevBuf::ensure(size_t bytes, size_t keep_bytes, cudaStream_t st) {
+    if (bytes <= cap && p != nullptr) return B200RAG_OK;
+    size_t ncap = cap + cap / 2;
+    if (ncap < bytes) ncap = bytes;
+    ncap = (ncap + 255) & ~(size_t)255;
+    if (ncap == 0) ncap = 256;
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        // retry with the exact size before giving up
+        ncap = (bytes + 255) & ~(size_t)255;
+        e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    }
+    if (p != nullptr) {
+        if (keep_bytes > 0) {
+            e = cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { cudaFree(np); return cuda_fail(e, "cudaMemcpyAsync(grow)"); }
+        }
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(np); return cuda_fail(e, "cudaStreamSynchronize(grow)"); }
+        cudaFree(p);
+    }
+    p = np;
+    cap = ncap;
+    return B200RAG_OK;
+}
+void DevBuf::release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+__global__ void offset_copy_i64_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t n,
+                                       int64_t offset) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + offset;
+}
+
+static int use_device(const Shard* s) {
+    B2_CUDA(cudaSetDevice(s->cfg.device));
+    return B200RAG_OK;
+}
+
+static int ensure_pinned(Shard* s, size_t bytes) {
+    if (bytes <= s->h_pinned_cap) return B200RAG_OK;
+    if (s->h_pinned != nullptr) { cudaStreamSynchronize(s->stream); cudaFreeHost(s->h_pinned); s->h_pinned = nullptr; }
+    size_t ncap = std::max(bytes * 2, (size_t)1 << 16);
+    B2_CUDA(cudaMallocHost(&s->h_pinned, ncap));
+    s->h_pinned_cap = ncap;
+    return B200RAG_OK;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
+                       const float* w, int64_t nnz, bool host) {
+    cudaStream_t st = s->stream;
+    const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t row_bytes = (size_t)s->dim * 2;
+    B2_TRY(s->dense.ensure((size_t)(s->n_rows + n) * row_bytes, (size_t)s->n_rows * row_bytes, st));
+    B2_TRY(s->fwd_ptr.ensure((size_t)(s->n_rows + n + 1) * 8, (size_t)(s->n_rows + 1) * 8, st));
+    B2_TRY(s->fwd_terms.ensure((size_t)(s->nnz + nnz + 1) * 4, (size_t)s->nnz * 4, st));
+    B2_TRY(s->fwd_w.ensure((size_t)(s->nnz + nnz + 1) * 4, (size_t)s->nnz * 4, st));
+    B2_CUDA(cudaMemcpyAsync(s->dense.as<uint8_t>() + (size_t)s->n_rows * row_bytes, dense, (size_t)n * row_bytes, kind, st));
+    int64_t* fp = s->fwd_ptr.as<int64_t>() + s->n_rows;  // fp[0] already holds s->nnz
+    if (indptr == nullptr) {
+        std::vector<int64_t> flat((size_t)n, s->nnz);
+        B2_CUDA(cudaMemcpyAsync(fp + 1, flat.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+    } else if (host) {
+        std::vector<int64_t> sh((size_t)n);
+        for (int64_t i = 0; i < n; ++i) sh[(size_t)i] = indptr[i + 1] + s->nnz;
+        B2_CUDA(cudaMemcpyAsync(fp + 1, sh.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        if (nnz > 0) {
+            B2_CUDA(cudaMemcpyAsync(s->fwd_terms.as<uint32_t>() + s->nnz, terms, (size_t)nnz * 4, kind, st));
+            B2_CUDA(cudaMemcpyAsync(s->fwd_w.as<float>() + s->nnz, w, (size_t)nnz * 4, kind, st));
+        }
+        B2_CUDA(cudaStreamSynchronize(st));
+    } else {
+        offset_copy_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fp + 1, indptr + 1, n, s->nnz);
+        B2_CUDA(cudaGetLastError());
+        if (nnz > 0) {
+            B2_CUDA(cudaMemcpyAsync(s->fwd_terms.as<uint32_t>() + s->nnz, terms, (size_t)nnz * 4, kind, st));
+            B2_CUDA(cudaMemcpyAsync(s->fwd_w.as<float>() + s->nnz, w, (size_t)nnz * 4, kind, st));
+        }
+        B2_CUDA(cudaStreamSynchronize(st));
+    }
+    s->n_rows += n;
+    s->nnz += nnz;
+    return B200RAG_OK;
+}
+
+static int default_slack(int L) { return std::max(16, L / 2); }
+
+static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
+    const b200rag_query& q = s->q;
+    cudaStream_t st = s->stream;
+    const int B = q.batch;
+    const int nlegs = q.mode == B200RAG_HYBRID ? 2 : 1;
+    const int L = q.mode == B200RAG_HYBRID ? 2 * q.top_k : q.top_k;
+    int slack = s->slack > 0 ? s->slack : default_slack(L);
+    int Lc = L + slack;
+    if (Lc > 3 * B200RAG_MAX_TOPK) Lc = 3 * B200RAG_MAX_TOPK;
+
+    B2_TRY(s->ws.thr.ensure((size_t)(B + 1) * 8, 0, st));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + B;
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, st));
+    B2_TRY(s->ws.exact.ensure((size_t)B * Lc * 8, 0, st));
+
+    const bool want_dense = q.mode != B200RAG_SPARSE;
+    const bool want_sparse = q.mode != B200RAG_DENSE;
+    if (want_sparse && s->built_rows != s->n_rows) B2_TRY(build_inverted(s));
+
+    int leg = 0;
+    if (want_dense) {
+        b200rag_cand* out = cands + (size_t)leg * B * L;
+        if (s->n_rows == 0) {
+            B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), st));
+        } else {
+            const int nl_max = dense_scan_nlists(s);
+            B2_TRY(s->ws.lists_a.ensure((size_t)B * nl_max * Lc * 8, 0, st));
+            B2_TRY(s->ws.lists_b.ensure((size_t)B * nl_max * Lc * 8, 0, st));
+            int nlists = 0;
+            B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
+            uint64_t* approx = nullptr;
+            B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
+            B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
+            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f,
+                                       q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, out, ambiguous));
+        }
+        ++leg;
+    }
+    if (want_sparse) {
+        b200rag_cand* out = cands + (size_t)leg * B * L;
+        if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) {
+            B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), st));
+        } else {
+            const size_t need = (size_t)B * s->n_blocks * Lc * 8;
+            B2_TRY(s->ws.lists_a.ensure(need, 0, st));
+            B2_TRY(s->ws.lists_b.ensure(need, 0, st));
+            B2_TRY(launch_sparse_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>()));
+            uint64_t* approx = nullptr;
+            B2_TRY(launch_merge_tree(s, B, (int)s->n_blocks, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
+            B2_TRY(launch_rescore_sparse(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
+            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 1e-12f, 4e-5f, 0, 0.f, out, ambiguous));
+        }
+        ++leg;
+    }
+    (void)nlegs;
+    return B200RAG_OK;
+}
+
+}  // namespace b200rag
+
+using namespace b200rag;
+
+extern "C" {
+
+const char* b200rag_version(void) { return "b200rag 0.1 (sm_100a)"; }
+const char* b200rag_last_error(void) { return g_err.c_str(); }
+
+int b200rag_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int b200rag_normalize_bf16(const float* x, int64_t n, int32_t dim, uint16_t* out) {
+    if (x == nullptr || out == nullptr || n < 0 || dim <= 0) { set_error("normalize: bad argument"); return B200RAG_ERR_INVALID; }
+    for (int64_t r = 0; r < n; ++r) {
+        const float* row = x + r * (int64_t)dim;
+        double ss = 0.0;
+        for (int k = 0; k < dim; ++k) {
+            const double v = (double)row[k];
+            if (!isfinite(v)) { set_error("normalize: non-finite input"); return B200RAG_ERR_INVALID; }
+            ss = ss + v * v;
+        }
+        double nrm = sqrt(ss);
+        if (nrm == 0.0) nrm = 1.0;
+        for (int k = 0; k < dim; ++k) {
+            const float y = (float)((double)row[k] / nrm);
+            uint32_t u;
+            memcpy(&u, &y, 4);
+            u = u + 0x7FFFu + ((u >> 16) & 1u);
+            out[r * (int64_t)dim + k] = (uint16_t)(u >> 16);
+        }
+    }
+    return B200RAG_OK;
+}
+
+int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
+    if (cfg == nullptr || out == nullptr) { set_error("shard_create: null argument"); return B200RAG_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->dim <= 0 || cfg->dim % 256 != 0 || cfg->dim > 1024) { set_error("shard_create: dim must be a multiple of 256, <= 1024"); return B200RAG_ERR_INVALID; }
+    if (cfg->vocab <= 0) { set_error("shard_create: vocab must be positive"); return B200RAG_ERR_INVALID; }
+    int R = cfg->docs_per_block == 0 ? 8192 : cfg->docs_per_block;
+    if (R < 1024 || R > 32768 || (R & (R - 1)) != 0) { set_error("shard_create: docs_per_block must be a power of two in [1024, 32768]"); return B200RAG_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: this library has no CPU fallback");
+        return B200RAG_ERR_NOGPU;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("shard_create: bad device ordinal"); return B200RAG_ERR_INVALID; }
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error(std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + ", this library is built for sm_100a only");
+        return B200RAG_ERR_NOGPU;
+    }
+    B2_CUDA(cudaSetDevice(cfg->device));
+    Shard* s = new Shard();
+    s->cfg = *cfg;
+    s->dim = cfg->dim;
+    s->vocab = cfg->vocab;
+    s->R = R;
+    s->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaStreamCreate"); }
+    s->stream = s->own_stream;
+    int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);
+    if (rc == B200RAG_OK) {
+        e = cudaMemsetAsync(s->fwd_ptr.p, 0, 8, s->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
+    }
+    if (rc == B200RAG_OK && cfg->reserve_rows > 0) rc = s->dense.ensure((size_t)cfg->reserve_rows * s->dim * 2, 0, s->stream);
+    if (rc == B200RAG_OK && cfg->reserve_postings > 0) {
+        rc = s->fwd_terms.ensure((size_t)cfg->reserve_postings * 4, 0, s->stream);
+        if (rc == B200RAG_OK) rc = s->fwd_w.ensure((size_t)cfg->reserve_postings * 4, 0, s->stream);
+    }
+    if (rc != B200RAG_OK) { b200rag_shard_destroy((b200rag_shard*)s); return rc; }
+    *out = (b200rag_shard*)s;
+    return B200RAG_OK;
+}
+
+void b200rag_shard_destroy(b200rag_shard* sp) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) return;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->stream);
+    s->dense.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
+    s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
+    for (auto& kv : s->masks) kv.second.release();
+    s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
+    s->ws.exact.release(); s->ws.cands.release(); s->ws.out.release();
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+int b200rag_set_stream(b200rag_shard* sp, void* stream) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    s->stream = stream != nullptr ? (cudaStream_t)stream : s->own_stream;
+    return B200RAG_OK;
+}
+
+int b200rag_set_slack(b200rag_shard* sp, int32_t slack) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || slack < 0) { set_error("set_slack: bad argument"); return B200RAG_ERR_INVALID; }
+    s->slack = slack;
+    return B200RAG_OK;
+}
+
+int b200rag_sync(b200rag_shard* sp) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B200RAG_OK;
+}
+
+int b200rag_add(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
+                const float* w) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || n < 0 || (n > 0 && dense == nullptr)) { set_error("add: bad argument"); return B200RAG_ERR_INVALID; }
+    if (n == 0) return B200RAG_OK;
+    if (s->n_rows + n > 0xFFFFFFF0ll) { set_error("add: shard row limit (2^32) exceeded"); return B200RAG_ERR_INVALID; }
+    int64_t nnz = 0;
+    if (indptr != nullptr) {
+        if (indptr[0] != 0) { set_error("add: sparse indptr must start at 0"); return B200RAG_ERR_INVALID; }
+        nnz = indptr[n];
+        if (nnz > 0 && (terms == nullptr || w == nullptr)) { set_error("add: sparse terms/weights missing"); return B200RAG_ERR_INVALID; }
+        for (int64_t d = 0; d < n; ++d) {
+            if (indptr[d + 1] < indptr[d]) { set_error("add: sparse indptr not monotone"); return B200RAG_ERR_INVALID; }
+            for (int64_t i = indptr[d]; i < indptr[d + 1]; ++i) {
+                if (terms[i] >= (uint32_t)s->vocab) { set_error("add: sparse index out of vocabulary range"); return B200RAG_ERR_INVALID; }
+                if (i > indptr[d] && terms[i] <= terms[i - 1]) { set_error("add: sparse indices must be ascending and unique per row"); return B200RAG_ERR_INVALID; }
+                if (!isfinite(w[i])) { set_error("add: non-finite sparse weight"); return B200RAG_ERR_INVALID; }
+            }
+        }
+    }
+    B2_TRY(use_device(s));
+    return append_rows(s, n, dense, indptr, terms, w, nnz, true);
+}
+
+int b200rag_add_device(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr,
+                       const uint32_t* terms, const float* w, int64_t nnz) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || n < 0 || nnz < 0 || (n > 0 && dense == nullptr)) { set_error("add_device: bad argument"); return B200RAG_ERR_INVALID; }
+    if (n == 0) return B200RAG_OK;
+    if (s->n_rows + n > 0xFFFFFFF0ll) { set_error("add_device: shard row limit (2^32) exceeded"); return B200RAG_ERR_INVALID; }
+    if (indptr == nullptr) nnz = 0;
+    B2_TRY(use_device(s));
+    return append_rows(s, n, dense, indptr, terms, w, nnz, false);
+}
+
+int b200rag_build(b200rag_shard* sp) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    return build_inverted(s);
+}
+
+int64_t b200rag_count(const b200rag_shard* sp) { return sp ? ((const Shard*)sp)->n_rows : 0; }
+int64_t b200rag_postings(const b200rag_shard* sp) { return sp ? ((const Shard*)sp)->nnz : 0; }
+
+int b200rag_clear(b200rag_shard* sp) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    s->n_rows = 0; s->nnz = 0; s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0;
+    s->h_blk_base.clear();
+    s->staged = false;
+    for (auto& kv : s->masks) kv.second.release();
+    s->masks.clear(); s->mask_rows.clear();
+    return B200RAG_OK;
+}
+
+int b200rag_read_dense(b200rag_shard* sp, int64_t row, int64_t n, uint16_t* out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || row < 0 || n < 0 || row + n > s->n_rows || out == nullptr) { set_error("read_dense: bad range"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaMemcpyAsync(out, s->dense.as<uint16_t>() + (size_t)row * s->dim, (size_t)n * s->dim * 2, cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B200RAG_OK;
+}
+
+static int mask_store(Shard* s, int32_t id, const uint32_t* words, int64_t n_rows, bool host) {
+    if (id < 0 || words == nullptr || n_rows < 0) { set_error("mask_set: bad argument"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    // sized to whole inverted-index blocks so kernels may read any word of a touched block
+    const int64_t cover = std::max<int64_t>(((std::max(n_rows, s->n_rows) + 32767) / 32768) * 32768, 32768);
+    const size_t words_total = (size_t)(cover / 32);
+    const size_t words_in = (size_t)((n_rows + 31) / 32);
+    DevBuf& b = s->masks[id];
+    B2_TRY(b.ensure(words_total * 4, 0, s->stream));
+    B2_CUDA(cudaMemsetAsync(b.p, 0, b.cap, s->stream));
+    if (words_in > 0)
+        B2_CUDA(cudaMemcpyAsync(b.p, words, words_in * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    s->mask_rows[id] = n_rows;
+    return B200RAG_OK;
+}
+
+int b200rag_mask_set(b200rag_shard* sp, int32_t id, const uint32_t* words, int64_t n_rows) {
+    if (sp == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    return mask_store((Shard*)sp, id, words, n_rows, true);
+}
+int b200rag_mask_set_device(b200rag_shard* sp, int32_t id, const uint32_t* words, int64_t n_rows) {
+    if (sp == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    return mask_store((Shard*)sp, id, words, n_rows, false);
+}
+int b200rag_mask_drop(b200rag_shard* sp, int32_t id) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    auto it = s->masks.find(id);
+    if (it == s->masks.end()) return B200RAG_OK;
+    use_device(s);
+    cudaStreamSynchronize(s->stream);
+    it->second.release();
+    s->masks.erase(it);
+    s->mask_rows.erase(id);
+    return B200RAG_OK;
+}
+
+int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L) {
+    if (q == nullptr) { set_error("null query"); return B200RAG_ERR_INVALID; }
+    if (nlegs) *nlegs = q->mode == B200RAG_HYBRID ? 2 : 1;
+    if (L) *L = q->mode == B200RAG_HYBRID ? 2 * q->top_k : q->top_k;
+    return B200RAG_OK;
+}
+
+int b200rag_stage(b200rag_shard* sp, const b200rag_query* q) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || q == nullptr) { set_error("stage: null argument"); return B200RAG_ERR_INVALID; }
+    if (q->mode < 0 || q->mode > 2) { set_error("stage: bad mode"); return B200RAG_ERR_INVALID; }
+    if (q->batch < 1 || q->batch > 65535) { set_error("stage: batch must be in [1, 65535]"); return B200RAG_ERR_INVALID; }
+    if (q->top_k < 1 || q->top_k > B200RAG_MAX_TOPK) { set_error("stage: top_k out of range"); return B200RAG_ERR_INVALID; }
+    const int B = q->batch;
+    const bool need_dense = q->mode != B200RAG_SPARSE, need_sparse = q->mode != B200RAG_DENSE;
+    if (need_dense && q->q_dense_bits == nullptr) { set_error("stage: dense query missing"); return B200RAG_ERR_INVALID; }
+    int64_t nt = 0;
+    if (need_sparse) {
+        if (q->q_sp_indptr == nullptr || q->q_sp_indptr[0] != 0) { set_error("stage: sparse query indptr missing or not starting at 0"); return B200RAG_ERR_INVALID; }
+        nt = q->q_sp_indptr[B];
+        if (nt > 0 && (q->q_sp_terms == nullptr || q->q_sp_weights == nullptr)) { set_error("stage: sparse query terms missing"); return B200RAG_ERR_INVALID; }
+        for (int b = 0; b < B; ++b) {
+            if (q->q_sp_indptr[b + 1] < q->q_sp_indptr[b]) { set_error("stage: sparse query indptr not monotone"); return B200RAG_ERR_INVALID; }
+            for (int64_t i = q->q_sp_indptr[b]; i < q->q_sp_indptr[b + 1]; ++i) {
+                if (q->q_sp_terms[i] >= (uint32_t)s->vocab) { set_error("stage: sparse query index out of vocabulary range"); return B200RAG_ERR_INVALID; }
+                if (i > q->q_sp_indptr[b] && q->q_sp_terms[i] <= q->q_sp_terms[i - 1]) { set_error("stage: sparse query indices must be ascending and unique"); return B200RAG_ERR_INVALID; }
+            }
+        }
+    }
+    B2_TRY(use_device(s));
+    s->h_masks.clear();
+    bool any_mask = false;
+    if (q->mask_ids != nullptr)
+        for (int b = 0; b < B; ++b) any_mask |= q->mask_ids[b] >= 0;
+    if (any_mask) {
+        s->h_masks.resize((size_t)B, nullptr);
+        for (int b = 0; b < B; ++b) {
+            const int32_t id = q->mask_ids[b];
+            if (id < 0) continue;
+            auto it = s->masks.find(id);
+            if (it == s->masks.end()) { set_error("stage: unknown mask id"); return B200RAG_ERR_INVALID; }
+            if ((size_t)(((s->n_rows + 32767) / 32768) * 32768 / 32) * 4 > it->second.cap) {
+                set_error("stage: mask is older than the shard (rows were added since mask_set)");
+                return B200RAG_ERR_STATE;
+            }
+            s->h_masks[(size_t)b] = it->second.as<const uint32_t>();
+        }
+    }
+    // one pinned staging block -> one H2D
+    const size_t o_bits = 0;
+    const size_t o_ind = al256(o_bits + (need_dense ? (size_t)B * s->dim * 2 : 0));
+    const size_t o_terms = al256(o_ind + (size_t)(B + 1) * 8);
+    const size_t o_w = al256(o_terms + (size_t)nt * 4);
+    const size_t o_masks = al256(o_w + (size_t)nt * 4);
+    const size_t total = al256(o_masks + (size_t)B * 8);
+    B2_TRY(ensure_pinned(s, total + (size_t)B * q->top_k * 16 + (size_t)(B + 1) * 4 + 1024));
+    B2_TRY(s->ws.q_stage.ensure(total, 0, s->stream));
+    // the previous batch's H2D must have drained before the pinned block is rewritten
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    uint8_t* h = (uint8_t*)s->h_pinned;
+    if (need_dense) memcpy(h + o_bits, q->q_dense_bits, (size_t)B * s->dim * 2);
+    if (need_sparse) {
+        memcpy(h + o_ind, q->q_sp_indptr, (size_t)(B + 1) * 8);
+        if (nt > 0) {
+            memcpy(h + o_terms, q->q_sp_terms, (size_t)nt * 4);
+            memcpy(h + o_w, q->q_sp_weights, (size_t)nt * 4);
+        }
+    } else {
+        memset(h + o_ind, 0, (size_t)(B + 1) * 8);
+    }
+    if (any_mask) memcpy(h + o_masks, s->h_masks.data(), (size_t)B * 8);
+    else memset(h + o_masks, 0, (size_t)B * 8);
+    B2_CUDA(cudaMemcpyAsync(s->ws.q_stage.p, h, total, cudaMemcpyHostToDevice, s->stream));
+    uint8_t* d = s->ws.q_stage.as<uint8_t>();
+    s->ws.q_bits.p = d + o_bits;
+    s->ws.q_sp_indptr.p = d + o_ind;
+    s->ws.q_sp_terms.p = d + o_terms;
+    s->ws.q_sp_w.p = d + o_w;
+    s->ws.q_masks.p = d + o_masks;
+    s->q = *q;
+    if (s->q.rrf_k <= 0) s->q.rrf_k = 2;
+    s->q.q_dense_bits = nullptr; s->q.q_sp_indptr = nullptr; s->q.q_sp_terms = nullptr; s->q.q_sp_weights = nullptr; s->q.mask_ids = nullptr;
+    s->staged_q_terms = nt;
+    s->staged = true;
+    return B200RAG_OK;
+}
+
+int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || cands_dev == nullptr) { set_error("legs: null argument"); return B200RAG_ERR_INVALID; }
+    if (!s->staged) { set_error("legs: no staged query batch"); return B200RAG_ERR_STATE; }
+    B2_TRY(use_device(s));
+    s->stats = b200rag_stats{};
+    return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
+}
+
+int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int64_t* out_ids, double* out_scores,
+                 int32_t* out_counts) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || gathered == nullptr || n_shards < 1 || out_ids == nullptr || out_scores == nullptr || out_counts == nullptr) {
+        set_error("fuse: bad argument");
+        return B200RAG_ERR_INVALID;
+    }
+    if (!s->staged) { set_error("fuse: no staged query batch"); return B200RAG_ERR_STATE; }
+    B2_TRY(use_device(s));
+    const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
+    return launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
+                       out_ids, out_scores, out_counts);
+}
+
+int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, double* out_scores,
+                   int32_t* out_counts) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || q == nullptr || out_ids == nullptr || out_scores == nullptr || out_counts == nullptr) {
+        set_error("search: null argument");
+        return B200RAG_ERR_INVALID;
+    }
+    B2_TRY(b200rag_stage(sp, q));
+    cudaStream_t st = s->stream;
+    const int B = s->q.batch, K = s->q.top_k;
+    const int nlegs = s->q.mode == B200RAG_HYBRID ? 2 : 1;
+    const int L = s->q.mode == B200RAG_HYBRID ? 2 * K : K;
+    B2_TRY(s->ws.cands.ensure((size_t)nlegs * B * L * sizeof(b200rag_cand), 0, st));
+    const size_t o_ids = 0, o_sc = (size_t)B * K * 8, o_cnt = o_sc + (size_t)B * K * 8;
+    const size_t out_bytes = o_cnt + (size_t)(B + 1) * 4;
+    B2_TRY(s->ws.out.ensure(out_bytes, 0, st));
+    uint8_t* d = s->ws.out.as<uint8_t>();
+    int32_t* amb = (int32_t*)(d + o_cnt) + B;
+    const int saved_slack = s->slack;
+    int retries = 0;
+    int launches = 0;
+    int rc = B200RAG_OK;
+    // results land in the tail of the pinned block (the head still feeds the query H2D)
+    uint8_t* hres = (uint8_t*)s->h_pinned + (s->h_pinned_cap - al256(out_bytes) - 256);
+    hres = (uint8_t*)(((uintptr_t)hres) & ~(uintptr_t)255);
+    for (;;) {
+        s->stats = b200rag_stats{};
+        {
+            cudaError_t me = cudaMemsetAsync(amb, 0, 4, st);
+            if (me != cudaSuccess) { rc = cuda_fail(me, "cudaMemsetAsync(ambiguous)"); break; }
+        }
+        rc = run_legs(s, s->ws.cands.as<b200rag_cand>(), amb);
+        if (rc != B200RAG_OK) break;
+        rc = launch_fuse(s, s->q.mode, B, L, K, s->q.rrf_k, s->ws.cands.as<b200rag_cand>(), 1, (int64_t*)(d + o_ids),
+                         (double*)(d + o_sc), (int32_t*)(d + o_cnt));
+        if (rc != B200RAG_OK) break;
+        cudaError_t e = cudaMemcpyAsync(hres, d, out_bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "result read-back"); break; }
+        launches += s->stats.kernel_launches;
+        const int32_t ambiguous = ((const int32_t*)(hres + o_cnt))[B];
+        const int cur = s->slack > 0 ? s->slack : default_slack(L);
+        if (ambiguous == 0 || L + cur >= 3 * B200RAG_MAX_TOPK || retries >= 6) break;
+        s->slack = std::min(cur * 2 + L, 3 * B200RAG_MAX_TOPK - L);  // widen and redo the legs
+        ++retries;
+    }
+    s->slack = saved_slack;
+    if (rc != B200RAG_OK) return rc;
+    memcpy(out_ids, hres + o_ids, (size_t)B * K * 8);
+    memcpy(out_scores, hres + o_sc, (size_t)B * K * 8);
+    memcpy(out_counts, hres + o_cnt, (size_t)B * 4);
+    s->stats.kernel_launches = launches;
+    s->stats.retries = retries;
+    return B200RAG_OK;
+}
+
+int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
+    if (sp == nullptr || out == nullptr) { set_error("get_stats: null argument"); return B200RAG_ERR_INVALID; }
+    *out = ((const Shard*)sp)->stats;
+    return B200RAG_OK;
+}
+
+int b200rag_synth_dense(b200rag_shard* sp, uint64_t seed, int64_t row0, int64_t n, uint16_t* out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || out == nullptr || n < 0) { set_error("synth_dense: bad argument"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    return launch_synth_dense(s->stream, seed, row0, n, s->dim, out);
+}
+
+int b200rag_synth_sparse(b200rag_shard* sp, uint64_t seed, int64_t row0, int64_t n, int32_t doc_tokens,
+                         const uint64_t* thr, const float* idf, const float* tff, int64_t term_mul, int64_t* counts,
+                         const int64_t* indptr, uint32_t* terms, float* weights) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || thr == nullptr || n < 0) { set_error("synth_sparse: bad argument"); return B200RAG_ERR_INVALID; }
+    if (counts == nullptr && (indptr == nullptr || terms == nullptr || weights == nullptr || idf == nullptr || tff == nullptr)) {
+        set_error("synth_sparse: fill pass needs indptr/terms/weights/idf/tff");
+        return B200RAG_ERR_INVALID;
+    }
+    B2_TRY(use_device(s));
+    return launch_synth_sparse(s->stream, seed, row0, n, s->vocab, doc_tokens, thr, idf, tff, term_mul, counts, indptr,
+                               terms, weights);
+}
+
+int b200rag_exclusive_scan_i64(b200rag_shard* sp, const int64_t* in, int64_t n, int64_t* out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || in == nullptr || out == nullptr || n < 0) { set_error("scan: bad argument"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    return launch_exclusive_scan_i64(s->stream, in, n, out);
+}
+
+int b200rag_synth_collection_mask(b200rag_shard* sp, uint64_t seed, int64_t row0, int64_t n, const uint64_t* thr,
+                                  int32_t n_coll, int32_t coll, uint32_t* out_words) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || thr == nullptr || out_words == nullptr || n < 0) { set_error("collection_mask: bad argument"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    return launch_synth_collection_mask(s->stream, seed, row0, n, thr, n_coll, coll, out_words);
+}
+
+}  // extern "C"

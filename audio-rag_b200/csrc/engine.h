@@ -1,0 +1,144 @@
+// Internal layout of a shard and the launchers each .cu exports to engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rag.h"
+
+namespace b200rag {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B2_CUDA(call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+    } while (0)
+#define B2_TRY(call)                       \
+    do {                                   \
+        int rc__ = (call);                 \
+        if (rc__ != B200RAG_OK) return rc__; \
+    } while (0)
+
+// Growable device array (geometric growth, contents preserved).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;  // bytes
+    int ensure(size_t bytes, size_t keep_bytes, cudaStream_t st);
+    void release();
+    template <typename T>
+    T* as() const { return (T*)p; }
+};
+
+constexpr int kMaxBatchMasks = 4096;
+constexpr int kScanConsumerWarps = 8;
+constexpr int kScanTileRows = 16;
+constexpr int kSparseThreads = 512;
+constexpr int kMaxQueryTermsChunk = 256;
+constexpr int kMergeMaxKeys = 8192;
+
+struct DevPtr {
+    void* p = nullptr;
+    template <typename T>
+    T* as() const { return (T*)p; }
+};
+
+struct Workspace {
+    DevBuf q_stage;       // one H2D per batch: [q_bits | q_sp_indptr | q_sp_terms | q_sp_w | q_masks]
+    DevPtr q_bits;        // [B, dim] u16
+    DevPtr q_sp_indptr;   // [B+1] i64
+    DevPtr q_sp_terms;    // u32
+    DevPtr q_sp_w;        // f32
+    DevPtr q_masks;       // [B] const uint32_t*
+    DevBuf thr;           // [B] u64 running grid-wide thresholds (dense) + [1] u64 postings counter
+    DevPtr post_count;    // -> thr[B]
+    DevBuf lists_a;       // candidate key lists (ping)
+    DevBuf lists_b;       // candidate key lists (pong)
+    DevBuf exact;         // [B, Lc] u64 exact keys
+    DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
+    DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
+};
+
+struct Shard {
+    b200rag_config cfg{};
+    int dim = 0, vocab = 0, R = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int slack = 0;
+
+    // dense rows
+    int64_t n_rows = 0;
+    DevBuf dense;  // [n_rows, dim] bf16 bits
+
+    // forward (doc-major) sparse index, kept for the exact re-score and for rebuilds
+    int64_t nnz = 0;
+    DevBuf fwd_ptr;    // i64 [n_rows+1]
+    DevBuf fwd_terms;  // u32 [nnz]
+    DevBuf fwd_w;      // f32 [nnz]
+
+    // block-major inverted index: block b covers local docs [b*R, (b+1)*R)
+    int64_t built_rows = 0;  // rows covered by complete blocks + the trailing partial block as of last build
+    int64_t n_blocks = 0;
+    int64_t inv_nnz = 0;  // postings stored (block bases padded to 8)
+    DevBuf dir;           // u32 [n_blocks, vocab+1]  offsets relative to the block base
+    DevBuf blk_base;      // i64 [n_blocks+1]
+    DevBuf post_doc;      // u16 [inv_nnz] doc id within block
+    DevBuf post_w;        // f32 [inv_nnz]
+    std::vector<int64_t> h_blk_base;
+
+    // masks
+    std::map<int32_t, DevBuf> masks;
+    std::map<int32_t, int64_t> mask_rows;
+
+    // staged query batch
+    b200rag_query q{};
+    bool staged = false;
+    std::vector<const uint32_t*> h_masks;
+    int64_t staged_q_terms = 0;
+    std::vector<int64_t> h_q_indptr;
+
+    Workspace ws;
+    b200rag_stats stats{};
+
+    // pinned host staging for results
+    void* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+};
+
+// ---- dense_scan.cu -------------------------------------------------------------------------------------
+// SIMT bulk-copy scan: approximate fp32 scores, per-CTA top-Lc key lists.  Returns number of lists per query.
+int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, int* nlists);
+int dense_scan_nlists(const Shard* s);
+
+// ---- select.cu -----------------------------------------------------------------------------------------
+// Reduce [batch, n_lists, Lc] key lists to [batch, Lc] (sorted desc) with a tree of smem bitonic merges.
+// `a` holds the input; `a`/`b` are used ping-pong; *result points at the final [batch, Lc] list.
+int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uint64_t* b, uint64_t** result);
+int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact);
+int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact);
+// sort exact keys, apply threshold, slack guard, emit b200rag_cand [batch, L]
+int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
+                        float eps_abs, float eps_rel, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
+int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
+                int n_shards, int64_t* out_ids, double* out_scores, int32_t* out_counts);
+
+// ---- sparse.cu -----------------------------------------------------------------------------------------
+int build_inverted(Shard* s);
+int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, n_blocks, Lc]*/);
+
+// ---- synth.cu ------------------------------------------------------------------------------------------
+int launch_synth_dense(cudaStream_t st, uint64_t seed, int64_t row0, int64_t n, int dim, uint16_t* out);
+int launch_synth_sparse(cudaStream_t st, uint64_t seed, int64_t row0, int64_t n, int vocab, int doc_tokens,
+                        const uint64_t* thr, const float* idf, const float* tff, int64_t term_mul, int64_t* counts,
+                        const int64_t* indptr, uint32_t* terms, float* w);
+int launch_exclusive_scan_i64(cudaStream_t st, const int64_t* in, int64_t n, int64_t* out);
+int launch_synth_collection_mask(cudaStream_t st, uint64_t seed, int64_t row0, int64_t n, const uint64_t* thr,
+                                 int n_coll, int coll, uint32_t* out_words);
+
+}  // namespace b200rag

@@ -1,0 +1,348 @@
+// K3/K4  selection, exact re-score and fusion kernels.
+//
+//   merge_lists     tree of shared-memory bitonic merges over per-CTA / per-block candidate key lists
+//   rescore_dense   canonical fp64 score of the surviving candidates, bit-equal to the oracle
+//   rescore_sparse  canonical fp64 sparse score from the forward index
+//   finalize_leg    order by (score desc, row asc) (R5), apply score_threshold (R6), slack guard, emit candidates
+//   fuse            G-way merge of gathered per-shard legs (R5) + Reciprocal Rank Fusion (R9/R10); replaces
+//                   qdrant-client hybrid/fusion.py::reciprocal_rank_fusion as requested at
+//                   src/audio_rag/retrieval/qdrant.py:281-298 (FusionQuery(Fusion.RRF), limit=top_k)
+#include "common.cuh"
+#include "engine.h"
+
+namespace b200rag {
+
+// ------------------------------------------------------------------------------------------------ merge
+__global__ void __launch_bounds__(512) merge_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int Lc,
+                                                          uint64_t* __restrict__ out, int lists_per_group,
+                                                          int n_groups, int npow2) {
+    extern __shared__ __align__(16) uint64_t mkeys[];
+    const int q = blockIdx.y, g = blockIdx.x;
+    const int l0 = g * lists_per_group;
+    const int l1 = min(n_lists, l0 + lists_per_group);
+    const int cnt = (l1 - l0) * Lc;
+    const uint64_t* src = in + ((size_t)q * n_lists + l0) * Lc;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) mkeys[i] = i < cnt ? src[i] : 0ull;
+    cta_bitonic_desc(mkeys, npow2, threadIdx.x, blockDim.x, 0);
+    uint64_t* dst = out + ((size_t)q * n_groups + g) * Lc;
+    for (int i = threadIdx.x; i < Lc; i += blockDim.x) dst[i] = mkeys[i];
+}
+
+int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uint64_t* b, uint64_t** result) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kMergeMaxKeys * 8));
+        attr_set = true;
+    }
+    uint64_t* cur = a;
+    uint64_t* nxt = b;
+    while (n_lists > 1) {
+        int lpg = kMergeMaxKeys / Lc;
+        if (lpg < 2) lpg = 2;
+        if (lpg > n_lists) lpg = n_lists;
+        const int n_groups = (n_lists + lpg - 1) / lpg;
+        const int npow2 = next_pow2(lpg * Lc);
+        if (npow2 > kMergeMaxKeys) { set_error("merge: candidate list too long"); return B200RAG_ERR_INVALID; }
+        dim3 grid(n_groups, batch);
+        merge_lists_kernel<<<grid, 512, (size_t)npow2 * 8, s->stream>>>(cur, n_lists, Lc, nxt, lpg, n_groups, npow2);
+        B2_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        uint64_t* t = cur; cur = nxt; nxt = t;
+        n_lists = n_groups;
+    }
+    *result = cur;
+    return B200RAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ exact dense
+__device__ __forceinline__ double bf16lo_d(uint32_t u) { return (double)__uint_as_float(u << 16); }
+__device__ __forceinline__ double bf16hi_d(uint32_t u) { return (double)__uint_as_float(u & 0xFFFF0000u); }
+
+__global__ void __launch_bounds__(128) rescore_dense_kernel(const uint16_t* __restrict__ corpus, int dim,
+                                                            const uint16_t* __restrict__ q_bits,
+                                                            const uint64_t* __restrict__ approx,
+                                                            uint64_t* __restrict__ exact, int Lc) {
+    extern __shared__ __align__(16) double q64[];
+    const int q = blockIdx.x;
+    for (int k = threadIdx.x; k < dim; k += blockDim.x)
+        q64[k] = (double)__uint_as_float(((uint32_t)q_bits[(size_t)q * dim + k]) << 16);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Lc; i += blockDim.x) {
+        const uint64_t key = approx[(size_t)q * Lc + i];
+        uint64_t ek = 0;
+        if (key != 0) {
+            const uint32_t row = key_row(key);
+            const uint4* rp = reinterpret_cast<const uint4*>(corpus + (size_t)row * dim);
+            double acc = 0.0;
+            for (int k8 = 0; k8 < dim / 8; ++k8) {
+                const uint4 v = rp[k8];
+                const double* qq = q64 + k8 * 8;
+                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.x), qq[0]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.x), qq[1]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.y), qq[2]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.y), qq[3]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.z), qq[4]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.z), qq[5]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.w), qq[6]));
+                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.w), qq[7]));
+            }
+            ek = make_key(__double2float_rn(acc) + 0.0f, row);
+        }
+        exact[(size_t)q * Lc + i] = ek;
+    }
+}
+
+int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact) {
+    rescore_dense_kernel<<<batch, 128, (size_t)s->dim * 8, s->stream>>>(
+        s->dense.as<uint16_t>(), s->dim, s->ws.q_bits.as<uint16_t>(), approx, exact, Lc);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ exact sparse
+__global__ void __launch_bounds__(256) rescore_sparse_kernel(const int64_t* __restrict__ fwd_ptr,
+                                                             const uint32_t* __restrict__ fwd_terms,
+                                                             const float* __restrict__ fwd_w,
+                                                             const int64_t* __restrict__ q_indptr,
+                                                             const uint32_t* __restrict__ q_terms,
+                                                             const float* __restrict__ q_w,
+                                                             const uint64_t* __restrict__ approx,
+                                                             uint64_t* __restrict__ exact, int Lc) {
+    __shared__ uint32_t qt[kMaxQueryTermsChunk];
+    __shared__ float qw[kMaxQueryTermsChunk];
+    __shared__ double prod[8][kMaxQueryTermsChunk];
+    __shared__ uint8_t present[8][kMaxQueryTermsChunk];
+    const int q = blockIdx.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + w;
+    const uint64_t key = i < Lc ? approx[(size_t)q * Lc + i] : 0ull;
+    const bool active = key != 0;
+    const uint32_t row = key_row(key);
+    int64_t ds = 0, de = 0;
+    if (active) { ds = fwd_ptr[row]; de = fwd_ptr[row + 1]; }
+    const int64_t qs = q_indptr[q], qe = q_indptr[q + 1];
+    double acc = 0.0;
+    for (int64_t c0 = qs; c0 < qe; c0 += kMaxQueryTermsChunk) {
+        const int cn = (int)min((int64_t)kMaxQueryTermsChunk, qe - c0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cn; j += blockDim.x) { qt[j] = q_terms[c0 + j]; qw[j] = q_w[c0 + j]; }
+        __syncthreads();
+        if (active) {
+            for (int j = lane; j < cn; j += 32) {
+                const uint32_t t = qt[j];
+                int64_t lo = ds, hi = de;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (fwd_terms[mid] < t) lo = mid + 1; else hi = mid;
+                }
+                const bool hit = lo < de && fwd_terms[lo] == t;
+                present[w][j] = hit ? 1 : 0;
+                if (hit) prod[w][j] = __dmul_rn((double)qw[j], (double)fwd_w[lo]);
+            }
+            __syncwarp();
+            if (lane == 0)
+                for (int j = 0; j < cn; ++j)
+                    if (present[w][j]) acc = __dadd_rn(acc, prod[w][j]);
+            __syncwarp();
+        }
+    }
+    if (i < Lc && lane == 0)
+        exact[(size_t)q * Lc + i] = active ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
+}
+
+int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact) {
+    dim3 grid((Lc + 7) / 8, batch);
+    rescore_sparse_kernel<<<grid, 256, 0, s->stream>>>(s->fwd_ptr.as<int64_t>(), s->fwd_terms.as<uint32_t>(),
+                                                       s->fwd_w.as<float>(), s->ws.q_sp_indptr.as<int64_t>(),
+                                                       s->ws.q_sp_terms.as<uint32_t>(), s->ws.q_sp_w.as<float>(),
+                                                       approx, exact, Lc);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize leg
+__global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __restrict__ approx,
+                                                           const uint64_t* __restrict__ exact, int Lc, int L,
+                                                           int npow2, float eps_abs, float eps_rel, int has_thr,
+                                                           float thr, int64_t row_base, b200rag_cand* __restrict__ out,
+                                                           int32_t* __restrict__ ambiguous) {
+    extern __shared__ __align__(16) uint64_t fkeys[];
+    __shared__ int nvalid_s;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) nvalid_s = 0;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        uint64_t k = i < Lc ? exact[(size_t)q * Lc + i] : 0ull;
+        if (k != 0 && has_thr && key_score(k) < thr) k = 0;
+        fkeys[i] = k;
+    }
+    cta_bitonic_desc(fkeys, npow2, threadIdx.x, blockDim.x, 0);
+    int local = 0;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) local += fkeys[i] != 0 ? 1 : 0;
+    if (local) atomicAdd(&nvalid_s, local);
+    __syncthreads();
+    const int nvalid = nvalid_s;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const uint64_t k = fkeys[i];
+        b200rag_cand c;
+        c.id = k != 0 ? row_base + (int64_t)key_row(k) : -1;
+        c.score = k != 0 ? key_score(k) : 0.f;
+        c.valid = k != 0 ? 1u : 0u;
+        out[(size_t)q * L + i] = c;
+    }
+    if (threadIdx.x == 0 && ambiguous != nullptr) {
+        const uint64_t last = approx[(size_t)q * Lc + Lc - 1];
+        if (last != 0) {  // the approximate list was full: rows outside it exist, bounded by `a`
+            const float a = key_score(last);
+            bool have_bound = false;
+            float bound = 0.f;
+            if (nvalid >= L) { bound = key_score(fkeys[L - 1]); have_bound = true; }
+            else if (has_thr) { bound = thr; have_bound = true; }
+            if (!have_bound) {
+                atomicAdd(ambiguous, 1);  // fewer than L survivors although candidates were cut: widen
+            } else {
+                const float eps = eps_abs + eps_rel * fmaxf(fabsf(a), fabsf(bound));
+                if (a + eps >= bound) atomicAdd(ambiguous, 1);
+            }
+        }
+    }
+}
+
+int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
+                        float eps_abs, float eps_rel, int has_thr, float thr, b200rag_cand* out,
+                        int32_t* ambiguous) {
+    const int npow2 = next_pow2(Lc);
+    finalize_leg_kernel<<<batch, 256, (size_t)npow2 * 8, s->stream>>>(approx, exact, Lc, L, npow2, eps_abs, eps_rel,
+                                                                      has_thr, thr, s->cfg.row_base, out, ambiguous);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fuse
+__device__ __forceinline__ bool cand_better(const b200rag_cand& f, const b200rag_cand& e) {
+    const uint32_t fo = ord_f32(f.score), eo = ord_f32(e.score);
+    return fo > eo || (fo == eo && f.id < e.id);
+}
+
+// smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
+__global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
+                                                   int nlegs, int batch, int L, int top_k, int rrf_k,
+                                                   int64_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                                                   int32_t* __restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const int M = n_shards * L;
+    b200rag_cand* stage = reinterpret_cast<b200rag_cand*>(fsm);
+    int64_t* leg_id = reinterpret_cast<int64_t*>(stage + M);
+    float* leg_score = reinterpret_cast<float*>(leg_id + 2 * L);
+    double* fused = reinterpret_cast<double*>(leg_score + 2 * L);
+    int64_t* fid = reinterpret_cast<int64_t*>(fused + 2 * L);
+    int* ford = reinterpret_cast<int*>(fid + 2 * L);
+    __shared__ int leg_n[2];
+    __shared__ int total_s;
+    const int q = blockIdx.x;
+    if (threadIdx.x < 2) leg_n[threadIdx.x] = 0;
+    if (threadIdx.x == 0) total_s = 0;
+
+    for (int leg = 0; leg < nlegs; ++leg) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            const int sh = i / L, j = i - sh * L;
+            stage[i] = gathered[(((size_t)sh * nlegs + leg) * batch + q) * L + j];
+        }
+        __syncthreads();
+        int local = 0;
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            const b200rag_cand e = stage[i];
+            if (!e.valid) continue;
+            ++local;
+            int rank = 0;
+            for (int f = 0; f < M; ++f) {
+                const b200rag_cand o = stage[f];
+                if (o.valid && cand_better(o, e)) ++rank;
+            }
+            if (rank < L) { leg_id[leg * L + rank] = e.id; leg_score[leg * L + rank] = e.score; }
+        }
+        if (local) atomicAdd(&leg_n[leg], local);
+    }
+    __syncthreads();
+    const int nd = min(leg_n[0], L);
+
+    if (nlegs == 1) {
+        const int n = min(nd, top_k);
+        for (int i = threadIdx.x; i < top_k; i += blockDim.x) {
+            out_ids[(size_t)q * top_k + i] = i < n ? leg_id[i] : -1;
+            out_scores[(size_t)q * top_k + i] = i < n ? (double)leg_score[i] : 0.0;
+        }
+        if (threadIdx.x == 0) out_counts[q] = n;
+        return;
+    }
+
+    // Reciprocal rank fusion, qdrant constants: score = sum over legs of 1/(rrf_k + pos0)
+    const int ns = min(leg_n[1], L);
+    const int NE = nd + ns;
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        if (e < nd) {
+            const int64_t id = leg_id[e];
+            double sc = 1.0 / (double)(rrf_k + e);
+            for (int j = 0; j < ns; ++j)
+                if (leg_id[L + j] == id) { sc = sc + 1.0 / (double)(rrf_k + j); break; }
+            fused[e] = sc; fid[e] = id; ford[e] = e;
+        } else {
+            const int j = e - nd;
+            const int64_t id = leg_id[L + j];
+            bool dup = false;
+            for (int i = 0; i < nd; ++i)
+                if (leg_id[i] == id) { dup = true; break; }
+            fused[e] = dup ? -1.0 : 1.0 / (double)(rrf_k + j);
+            fid[e] = id; ford[e] = dup ? -1 : e;
+        }
+    }
+    __syncthreads();
+    int local = 0;
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        if (ford[e] < 0) continue;
+        ++local;
+        const double se = fused[e];
+        int rank = 0;
+        for (int f = 0; f < NE; ++f) {
+            if (ford[f] < 0) continue;
+            const double sf = fused[f];
+            if (sf > se || (sf == se && ford[f] < ford[e])) ++rank;
+        }
+        if (rank < top_k) {
+            out_ids[(size_t)q * top_k + rank] = fid[e];
+            out_scores[(size_t)q * top_k + rank] = se;
+        }
+    }
+    if (local) atomicAdd(&total_s, local);
+    __syncthreads();
+    const int n = min(total_s, top_k);
+    for (int i = n + threadIdx.x; i < top_k; i += blockDim.x) {
+        out_ids[(size_t)q * top_k + i] = -1;
+        out_scores[(size_t)q * top_k + i] = 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[q] = n;
+}
+
+int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
+                int n_shards, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
+    const int nlegs = mode == B200RAG_HYBRID ? 2 : 1;
+    const size_t M = (size_t)n_shards * L;
+    const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
+    if (smem > 200 * 1024) { set_error("fuse: n_shards * L too large"); return B200RAG_ERR_INVALID; }
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    fuse_kernel<<<batch, 256, smem, s->stream>>>(gathered, n_shards, nlegs, batch, L, top_k, rrf_k, out_ids,
+                                                 out_scores, out_counts);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
+}  // namespace b200rag

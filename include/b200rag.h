@@ -1,0 +1,168 @@
+/* b200rag.h -- C ABI of the B200-native hybrid retrieval shard engine.
+ *
+ * The reference (mohammedadnansohail1-pixel/audio-rag) has NO native boundary: its retrieval plugin
+ * `QdrantRetriever` (src/audio_rag/retrieval/qdrant.py:14-381) is Python and hands every request to the
+ * third-party qdrant-client.  This header is therefore the FFI a maintainer would bind *instead of*
+ * `qdrant_client.QdrantClient` inside that plugin; each entry point names the reference call it replaces.
+ * The Python binding that does so lives in audio-rag_b200/b200rag/_ffi.py (ctypes) and the plugin mirror
+ * in audio-rag_b200/b200rag/retriever.py; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (B200RAG_OK == 0) unless noted;
+ *     `b200rag_last_error()` returns a thread-local message for the last non-OK status
+ *     (the plugin turns it into audio_rag.core.RetrievalError, qdrant.py:351-352).
+ *   - one `b200rag_shard` == one row-range shard of the corpus on one GPU (one process per GPU).
+ *     Local row id == insertion order within the shard; global id = cfg.row_base + local.
+ *   - "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers are device memory on
+ *     the shard's GPU.  The library never takes ownership of caller memory.
+ *   - a shard is safe for serialised use from one thread at a time (the reference calls its retriever
+ *     from a single blocking handler, api/v1/query.py:18-27,104-115).
+ *   - there is no CPU fallback: every compute entry point fails with B200RAG_ERR_NOGPU without a device.
+ */
+#ifndef B200RAG_H
+#define B200RAG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RAG_OK 0
+#define B200RAG_ERR_INVALID 1 /* bad argument                                   */
+#define B200RAG_ERR_CUDA 2    /* a CUDA call failed (message has the cuda error)  */
+#define B200RAG_ERR_NOGPU 3   /* no usable sm_100 device                          */
+#define B200RAG_ERR_OOM 4     /* device allocation failed                         */
+#define B200RAG_ERR_STATE 5   /* call order violated (e.g. search before build)   */
+
+/* search_type of QdrantRetriever.search (qdrant.py:233,250,272,299,313) */
+#define B200RAG_DENSE 0
+#define B200RAG_SPARSE 1
+#define B200RAG_HYBRID 2
+
+#define B200RAG_MAX_TOPK 256 /* RetrievalConfig.top_k <= 100 (config/schema.py:62); hybrid legs are 2*top_k */
+
+typedef struct b200rag_shard b200rag_shard;
+
+typedef struct {
+    int32_t device;         /* CUDA ordinal                                                             */
+    int32_t dim;            /* embedding_dim (qdrant.py:24,99): multiple of 256, <= 1024                  */
+    int32_t vocab;          /* sparse index space (XLM-R ids from BGE-M3, embeddings/bge.py:95-102)        */
+    int32_t docs_per_block; /* doc-range block of the inverted index: power of two, 1024..32768 (0 = 8192) */
+    int64_t row_base;       /* global id of local row 0                                                  */
+    int64_t reserve_rows;   /* optional pre-allocation hints (0 = grow on demand)                        */
+    int64_t reserve_postings;
+} b200rag_config;
+
+/* One candidate of one leg as exchanged between shards (16 bytes, all-gathered as raw bytes). */
+typedef struct {
+    int64_t id;     /* global row id                                 */
+    float score;    /* exact leg score (fp32 of the fp64 canonical sum) */
+    uint32_t valid; /* 0 = padding                                    */
+} b200rag_cand;
+
+/* A batch of queries: the arguments of QdrantRetriever.search (qdrant.py:228-234) for `batch` queries. */
+typedef struct {
+    int32_t mode;          /* B200RAG_DENSE | SPARSE | HYBRID, after the plugin applied the fallback rules  */
+    int32_t batch;         /* number of queries (reference: 1)                                          */
+    int32_t top_k;         /* limit (qdrant.py:249,296,311,320)                                          */
+    int32_t rrf_k;         /* RRF ranking constant; 0 = qdrant's 2 (hybrid/fusion.py)                     */
+    int32_t has_threshold; /* score_threshold, dense legacy collections only (qdrant.py:331)            */
+    float score_threshold;
+    const uint16_t* q_dense_bits; /* host [batch, dim] bf16 bits of the UNIT query (b200rag_normalize_bf16)   */
+    const int64_t* q_sp_indptr;   /* host [batch+1]  (NULL when mode == DENSE)                               */
+    const uint32_t* q_sp_terms;   /* host, ascending & unique per query                                    */
+    const float* q_sp_weights;    /* host                                                                  */
+    const int32_t* mask_ids;      /* host [batch] eligibility mask per query, -1 = all rows; NULL = none   */
+} b200rag_query;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+const char* b200rag_version(void);
+const char* b200rag_last_error(void);
+int b200rag_device_count(void); /* number of sm_100 devices visible (0 without a GPU; never fails) */
+
+/* Host-only helper (no GPU): cosine pre-normalisation + bf16 rounding, the arithmetic of SURVEY R2.
+ * Replaces the normalisation qdrant applies to COSINE vectors (collection schema at qdrant.py:98-117).
+ * ss = sequential fp64 sum of squares; y = fp32(fp64(x)/sqrt(ss)); bits = RNE bf16(y); zero rows pass through. */
+int b200rag_normalize_bf16(const float* x_host, int64_t n, int32_t dim, uint16_t* out_bits_host);
+
+/* ---- shard lifetime  (replaces QdrantClient(...) construction, qdrant.py:35-54) ------------------------ */
+int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out);
+void b200rag_shard_destroy(b200rag_shard* s);
+int b200rag_set_stream(b200rag_shard* s, void* cuda_stream); /* run on the caller's stream (NULL = own stream) */
+int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximate candidates per leg before the
+                                                                exact re-score (0 = default max(16, L/2))      */
+int b200rag_sync(b200rag_shard* s);
+
+/* ---- ingest  (replaces client.upsert, qdrant.py:197-220) ---------------------------------------------- */
+/* Append n rows.  dense_bits: [n, dim] unit rows as bf16 bits.  Sparse part is doc-major CSR
+ * (indptr[n+1] from 0, terms ascending & unique per row, all < vocab); pass NULLs for dense-only rows. */
+int b200rag_add(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_host, const int64_t* sp_indptr_host,
+                const uint32_t* sp_terms_host, const float* sp_weights_host);
+/* Same with device-resident inputs (bulk / synthetic ingest). nnz = indptr[n]. */
+int b200rag_add_device(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_dev, const int64_t* sp_indptr_dev,
+                       const uint32_t* sp_terms_dev, const float* sp_weights_dev, int64_t nnz);
+/* Bring the block-major inverted index up to date with the rows added so far (incremental). */
+int b200rag_build(b200rag_shard* s);
+int64_t b200rag_count(const b200rag_shard* s);    /* rows in the shard (client.get_collection().points_count, qdrant.py:369-370) */
+int64_t b200rag_postings(const b200rag_shard* s); /* sparse non-zeros in the shard */
+/* Drop every row (delete_collection of the last collection, qdrant.py:354-363); keeps allocations. */
+int b200rag_clear(b200rag_shard* s);
+/* Test/debug read-back of stored rows. */
+int b200rag_read_dense(b200rag_shard* s, int64_t row, int64_t n, uint16_t* out_bits_host);
+
+/* ---- eligibility masks  (replace Filter(must=[FieldCondition...]) + the collection itself, qdrant.py:262-269) */
+/* Bit (r & 31) of word (r >> 5) set <=> local row r is eligible.  n_rows bits are read; rows beyond are ineligible. */
+int b200rag_mask_set(b200rag_shard* s, int32_t mask_id, const uint32_t* words_host, int64_t n_rows);
+int b200rag_mask_set_device(b200rag_shard* s, int32_t mask_id, const uint32_t* words_dev, int64_t n_rows);
+int b200rag_mask_drop(b200rag_shard* s, int32_t mask_id);
+
+/* ---- search  (replaces client.query_points, qdrant.py:281-332) ------------------------------------------ */
+/* Whole path on one shard with HOST buffers: stage -> legs -> fuse -> read back.
+ * out_ids [batch, top_k] global row ids, out_scores [batch, top_k] (fp64: leg score, or RRF fused score),
+ * out_counts [batch] results per query.  Returned order: score desc, stated tie-breaks. */
+int b200rag_search(b200rag_shard* s, const b200rag_query* q, int64_t* out_ids_host, double* out_scores_host,
+                   int32_t* out_counts_host);
+
+/* The same path in its three device stages, for multi-shard composition (one process per GPU):
+ *   stage : copy the query batch to the device (async on the shard's stream);
+ *   legs  : per-shard candidates, exact-scored & ordered; cands_dev is [nlegs, batch, L] b200rag_cand with
+ *           nlegs = 2 (dense, sparse) for HYBRID else 1, L = 2*top_k for HYBRID else top_k;
+ *           ambiguous_dev (device int32, may be NULL) is incremented when a leg's slack guard fails;
+ *   fuse  : merge `n_shards` gathered candidate sets [n_shards, nlegs, batch, L] under R5, then RRF under
+ *           R9/R10 (HYBRID), writing device results [batch, top_k]. */
+int b200rag_stage(b200rag_shard* s, const b200rag_query* q);
+int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L);
+int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
+int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int64_t* out_ids_dev,
+                 double* out_scores_dev, int32_t* out_counts_dev);
+
+/* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
+typedef struct {
+    int32_t kernel_launches;     /* kernels of this library launched by the last legs+fuse               */
+    int32_t dense_path;          /* 0 = none, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM                    */
+    int64_t dense_bytes;         /* algorithmic bytes of the dense leg (rows * dim * 2 per corpus pass)   */
+    int64_t sparse_postings;     /* postings of the query terms in this shard (sum over batch)            */
+    int32_t dense_passes;        /* corpus passes made for the batch                                      */
+    int32_t retries;             /* slack-guard retries inside b200rag_search                              */
+} b200rag_stats;
+int b200rag_get_stats(const b200rag_shard* s, b200rag_stats* out);
+
+/* ---- synthetic corpus generation on the device (bench / tests; twins of b200rag/synth.py) -------------- */
+int b200rag_synth_dense(b200rag_shard* s, uint64_t seed, int64_t global_row_start, int64_t n, uint16_t* out_bits_dev);
+/* Two-pass doc-major CSR generation: call with terms_dev == NULL to get counts_dev[n] (int64), scan them into
+ * indptr_dev[n+1] yourself (or use b200rag_exclusive_scan_i64), then call again to fill terms/weights. */
+int b200rag_synth_sparse(b200rag_shard* s, uint64_t seed, int64_t global_row_start, int64_t n, int32_t doc_tokens,
+                         const uint64_t* zipf_thresholds_dev, const float* idf_dev, const float* tff_dev,
+                         int64_t term_mul, int64_t* counts_dev, const int64_t* indptr_dev, uint32_t* terms_dev,
+                         float* weights_dev);
+int b200rag_exclusive_scan_i64(b200rag_shard* s, const int64_t* in_dev, int64_t n, int64_t* out_dev /* n+1 */);
+/* Mask for "collection id == c" over rows [0, n): rows drawn Zipf over n_collections (synth.row_collections). */
+int b200rag_synth_collection_mask(b200rag_shard* s, uint64_t seed, int64_t global_row_start, int64_t n,
+                                  const uint64_t* coll_thresholds_dev, int32_t n_collections, int32_t collection,
+                                  uint32_t* out_words_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RAG_H */

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Bar: chunk ids bit-exact under the stated tie-break (score desc, smaller row id first; RRF ties
+keep first-seen order), dense/sparse leg scores bit-equal to the oracle's fp32(fp64 canonical sum), RRF
+scores bit-equal fp64.  (The north star allows 1e-5 relative for fp32 accumulate; the engine re-scores its
+candidates in the oracle's own operation order, so the tolerance used here is 0.)"""
+import numpy as np
+import pytest
+
+from helpers import Corpus, assert_result_equal, oracle_search
+
+pytestmark = pytest.mark.gpu
+
+
+def _shard_from(c, gpu, **kw):
+    from b200rag import Shard
+    sh = Shard(dim=c.dim, vocab=c.vocab, device=gpu, row_base=kw.pop("row_base", 0), **kw)
+    sh.add(c.bits, c.indptr, c.terms, c.w)
+    return sh
+
+
+def _run_and_check(sh, c, mode, nq, top_k, masks=None, mask_ids=None, score_threshold=None, qid_start=0,
+                   n_tokens=12, batch=None):
+    from b200rag import normalize_bf16
+    qf, ip, tt, ww = c.queries(nq, qid_start=qid_start, n_tokens=n_tokens)
+    qb = normalize_bf16(qf)
+    batch = batch or nq
+    for s in range(0, nq, batch):
+        e = min(nq, s + batch)
+        sub_ip = ip[s:e + 1] - ip[s]
+        sub_t, sub_w = tt[ip[s]:ip[e]], ww[ip[s]:ip[e]]
+        mids = None if mask_ids is None else np.asarray(mask_ids[s:e], dtype=np.int32)
+        ids, scores, counts = sh.search(mode, top_k, qb[s:e], sub_ip, sub_t, sub_w, mask_ids=mids,
+                                        score_threshold=score_threshold)
+        for i in range(s, e):
+            elig = None
+            if mids is not None and mids[i - s] >= 0:
+                elig = masks[int(mids[i - s])]
+            ei, es = oracle_search(c, mode, qb[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]], elig, top_k,
+                                   score_threshold, row_base=sh.row_base)
+            assert_result_equal(ids[i - s], scores[i - s], int(counts[i - s]), ei, es,
+                                ctx=f"mode={mode} q={i} k={top_k} n={c.n}")
+
+
+def test_device_generators_match_host_twins(gpu):
+    import torch
+    from b200rag import Shard, synth
+    c = Corpus(3000, dim=1024, n_total=50_000, row_start=777)
+    sh = Shard(dim=1024, vocab=c.vocab, device=gpu)
+    dev = torch.device("cuda", gpu)
+    out = torch.empty((c.n, 1024), dtype=torch.int16, device=dev)
+    sh.synth_dense(c.seed, 777, c.n, out)
+    sh.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), c.bits)
+    thr = torch.from_numpy(c.thr.view(np.int64)).to(dev)
+    idf = torch.from_numpy(c.idf).to(dev)
+    tff = torch.from_numpy(c.tff).to(dev)
+    counts = torch.empty(c.n, dtype=torch.int64, device=dev)
+    mul = synth.TERM_PERM_MUL % c.vocab
+    sh.synth_sparse(c.seed, 777, c.n, 256, thr, idf, tff, mul, counts, None, None, None)
+    indptr = torch.empty(c.n + 1, dtype=torch.int64, device=dev)
+    sh.exclusive_scan_i64(counts, c.n, indptr)
+    sh.sync()
+    assert np.array_equal(indptr.cpu().numpy(), c.indptr)
+    nnz = int(indptr[-1].item())
+    terms = torch.empty(nnz, dtype=torch.int32, device=dev)
+    w = torch.empty(nnz, dtype=torch.float32, device=dev)
+    sh.synth_sparse(c.seed, 777, c.n, 256, thr, idf, tff, mul, None, indptr, terms, w)
+    sh.sync()
+    assert np.array_equal(terms.cpu().numpy().view(np.uint32), c.terms)
+    assert np.array_equal(w.cpu().numpy().view(np.uint32), c.w.view(np.uint32))
+    # collection masks
+    cthr = synth.zipf_thresholds(1000)
+    cthr_d = torch.from_numpy(cthr.view(np.int64)).to(dev)
+    words = torch.zeros((c.n + 31) // 32, dtype=torch.int32, device=dev)
+    sh.synth_collection_mask(c.seed, 777, c.n, cthr_d, 1000, 0, words)
+    sh.sync()
+    exp = synth.pack_mask(synth.row_collections(c.seed, 777, c.n, 1000, cthr) == 0)
+    assert np.array_equal(words.cpu().numpy().view(np.uint32), exp)
+    # read-back of stored rows is the identity
+    sh.add(c.bits[:100])
+    assert np.array_equal(sh.read_dense(0, 100), c.bits[:100])
+    sh.close()
+
+
+@pytest.mark.parametrize("dim", [256, 768, 1024])
+@pytest.mark.parametrize("nq,batch", [(4, 1), (4, 2), (3, 3)])
+def test_dense_parity(gpu, dim, nq, batch):
+    c = Corpus(20_011, dim=dim, sparse=False)
+    sh = _shard_from(c, gpu)
+    _run_and_check(sh, c, "dense", nq, 10, batch=batch)
+    sh.close()
+
+
+@pytest.mark.parametrize("top_k", [1, 5, 100])
+def test_dense_topk_sizes(gpu, top_k):
+    c = Corpus(9_973, dim=1024, sparse=False)
+    sh = _shard_from(c, gpu)
+    _run_and_check(sh, c, "dense", 3, top_k, batch=1)
+    sh.close()
+
+
+@pytest.mark.parametrize("R", [1024, 8192])
+def test_sparse_parity(gpu, R):
+    c = Corpus(20_011, dim=256, vocab=30_011)
+    sh = _shard_from(c, gpu, docs_per_block=R)
+    _run_and_check(sh, c, "sparse", 6, 10, batch=3)
+    _run_and_check(sh, c, "sparse", 2, 100, batch=2, qid_start=50)
+    sh.close()
+
+
+def test_sparse_long_queries_and_full_vocab(gpu):
+    c = Corpus(6_000, dim=256)              # V = 250 002
+    sh = _shard_from(c, gpu, docs_per_block=2048)
+    _run_and_check(sh, c, "sparse", 2, 10, n_tokens=12)
+    _run_and_check(sh, c, "sparse", 2, 10, n_tokens=256 + 200, qid_start=7)   # HyDE-sized query, > 1 term chunk
+    sh.close()
+
+
+def test_hybrid_parity_config1(gpu):
+    """BASELINE config 1: hybrid, 10k chunks, single query, top_k = 5."""
+    c = Corpus(10_000, dim=1024)
+    sh = _shard_from(c, gpu)
+    _run_and_check(sh, c, "hybrid", 8, 5, batch=1)
+    _run_and_check(sh, c, "hybrid", 4, 10, batch=4, qid_start=100)
+    sh.close()
+
+
+def test_masks_both_legs(gpu):
+    from b200rag import synth
+    c = Corpus(12_345, dim=256, vocab=30_011)
+    sh = _shard_from(c, gpu, docs_per_block=4096)
+    coll = synth.row_collections(c.seed, 0, c.n, 7)
+    masks = {}
+    for m in range(7):
+        masks[m] = coll == m
+        sh.mask_set(m, synth.pack_mask(masks[m]), c.n)
+    mask_ids = [0, 3, -1, 6, 1, 2]
+    for mode in ("dense", "sparse", "hybrid"):
+        _run_and_check(sh, c, mode, 6, 10, masks=masks, mask_ids=mask_ids, batch=3)
+    # a mask with fewer eligible rows than top_k, and an empty one
+    small = np.zeros(c.n, dtype=bool)
+    small[[5, 77, 4000]] = True
+    masks[10] = small
+    masks[11] = np.zeros(c.n, dtype=bool)
+    sh.mask_set(10, synth.pack_mask(small), c.n)
+    sh.mask_set(11, synth.pack_mask(masks[11]), c.n)
+    for mode in ("dense", "sparse", "hybrid"):
+        _run_and_check(sh, c, mode, 2, 10, masks=masks, mask_ids=[10, 11], batch=2)
+    sh.close()
+
+
+def test_edge_cases(gpu):
+    from b200rag import Shard, normalize_bf16
+    from oracle import oracle
+    dim = 256
+    sh = Shard(dim=dim, vocab=1000, device=gpu, docs_per_block=1024)
+    q = normalize_bf16(np.ones((1, dim), np.float32))
+    sp = (np.array([0, 2]), np.array([3, 9], np.uint32), np.array([1.0, 2.0], np.float32))
+    # empty shard (R11: unknown/empty collection -> [])
+    for mode in ("dense", "sparse", "hybrid"):
+        ids, scores, counts = sh.search(mode, 5, q, *sp)
+        assert counts[0] == 0
+    # duplicate rows: exact ties resolve to the smaller row id; more duplicates than top_k + slack
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((40, dim)).astype(np.float32)
+    rows = np.concatenate([base, np.repeat(base[:1], 80, axis=0), base[1:3]])
+    bits = normalize_bf16(rows)
+    # sparse: rows 0..9 share term 3 with weight 0 (touched, score 0.0), row 10 has term 9, others nothing
+    indptr = [0]
+    terms, w = [], []
+    for r in range(len(rows)):
+        if r < 10:
+            terms.append(3); w.append(0.0)
+        elif r == 10:
+            terms += [3, 9]; w += [0.5, 1.5]
+        indptr.append(len(terms))
+    sh.add(bits, np.array(indptr), np.array(terms, np.uint32), np.array(w, np.float32))
+    oi = oracle.OracleIndex(dim)
+    oi.add_bits(bits, np.array(indptr), np.array(terms, np.uint32), np.array(w, np.float32))
+    qq = normalize_bf16(base[:1])
+    for mode, k in (("dense", 10), ("dense", 100), ("sparse", 5), ("sparse", 20), ("hybrid", 5), ("hybrid", 30)):
+        ids, scores, counts = sh.search(mode, k, qq, *sp)
+        ei, es = oi.search(mode, qq[0], sp[1], sp[2], None, k)
+        assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx=f"edge {mode} k={k}")
+    st = sh.stats()
+    # score_threshold (dense legacy collections, qdrant.py:331)
+    ids, scores, counts = sh.search("dense", 100, qq, score_threshold=0.9)
+    ei, es = oi.search("dense", qq[0], None, None, None, 100, score_threshold=0.9)
+    assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx="threshold")
+    assert counts[0] == 81
+    # query with no sparse terms in a hybrid batch (ragged): sparse leg empty -> RRF over the dense leg alone
+    sp2 = (np.array([0, 0, 2]), sp[1], sp[2])
+    q2 = np.concatenate([qq, normalize_bf16(base[5:6])])
+    ids, scores, counts = sh.search("hybrid", 5, q2, *sp2)
+    ei, es = oi.search("hybrid", q2[0], np.zeros(0, np.int64), np.zeros(0, np.float32), None, 5)
+    assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx="ragged q0")
+    ei, es = oi.search("hybrid", q2[1], sp[1], sp[2], None, 5)
+    assert_result_equal(ids[1], scores[1], int(counts[1]), ei, es, ctx="ragged q1")
+    # invalid inputs fail loudly
+    from b200rag import B200RagError
+    with pytest.raises(B200RagError):
+        sh.search("sparse", 5, qq, np.array([0, 2]), np.array([9, 3], np.uint32), np.array([1, 1], np.float32))
+    with pytest.raises(B200RagError):
+        sh.search("sparse", 5, qq, np.array([0, 1]), np.array([1000], np.uint32), np.array([1], np.float32))
+    with pytest.raises(B200RagError):
+        sh.search("dense", 0, qq)
+    assert st["kernel_launches"] > 0
+    sh.close()
+
+
+def test_incremental_add_and_rebuild(gpu):
+    c = Corpus(9_000, dim=256, vocab=30_011)
+    from b200rag import Shard
+    sh = Shard(dim=256, vocab=c.vocab, device=gpu, docs_per_block=2048)
+    cuts = [0, 1500, 1501, 5000, 9000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ip = c.indptr[a:b + 1] - c.indptr[a]
+        sh.add(c.bits[a:b], ip, c.terms[c.indptr[a]:c.indptr[b]], c.w[c.indptr[a]:c.indptr[b]])
+        sub = Corpus.__new__(Corpus)
+        sub.__dict__.update(c.__dict__)
+        sub.n = b
+        sub.bits, sub.indptr = c.bits[:b], c.indptr[:b + 1]
+        sub.terms, sub.w = c.terms[:c.indptr[b]], c.w[:c.indptr[b]]
+        _run_and_check(sh, sub, "hybrid", 2, 5, batch=2)
+    assert sh.count == 9000 and sh.postings == len(c.terms)
+    sh.clear()
+    assert sh.count == 0
+    sh.close()
+
+
+def test_two_shards_fuse_equals_one(gpu):
+    """Row-sharded composition (stage -> legs per shard -> concatenate -> fuse) == single shard, bit for bit."""
+    import torch
+    from b200rag import Shard, normalize_bf16
+    from b200rag._ffi import CAND_DTYPE
+    c = Corpus(16_000, dim=256, vocab=30_011)
+    cut = 6_500
+    one = _shard_from(c, gpu, docs_per_block=2048)
+    a = Shard(dim=256, vocab=c.vocab, device=gpu, row_base=0, docs_per_block=2048)
+    b = Shard(dim=256, vocab=c.vocab, device=gpu, row_base=cut, docs_per_block=2048)
+    a.add(c.bits[:cut], c.indptr[:cut + 1], c.terms[:c.indptr[cut]], c.w[:c.indptr[cut]])
+    b.add(c.bits[cut:], c.indptr[cut:] - c.indptr[cut], c.terms[c.indptr[cut]:], c.w[c.indptr[cut]:])
+    qf, ip, tt, ww = c.queries(5)
+    qb = normalize_bf16(qf)
+    dev = torch.device("cuda", gpu)
+    for mode, k in (("dense", 10), ("sparse", 10), ("hybrid", 10)):
+        ids1, sc1, cnt1 = one.search(mode, k, qb, ip, tt, ww)
+        q, keep = a.make_query(mode, k, qb, ip, tt, ww)
+        nlegs, L = Shard.legs_len(q)
+        gathered = torch.zeros((2, nlegs, 5, L, 2), dtype=torch.int64, device=dev)
+        amb = torch.zeros(1, dtype=torch.int32, device=dev)
+        for r, sh in enumerate((a, b)):
+            sh.stage(q, keep)
+            sh.legs(gathered[r], amb)
+            sh.sync()
+        out_ids = torch.empty((5, k), dtype=torch.int64, device=dev)
+        out_sc = torch.empty((5, k), dtype=torch.float64, device=dev)
+        out_cnt = torch.empty(5, dtype=torch.int32, device=dev)
+        a.fuse(gathered, 2, out_ids, out_sc, out_cnt)
+        a.sync()
+        assert int(amb.item()) == 0
+        assert np.array_equal(out_cnt.cpu().numpy(), cnt1)
+        assert np.array_equal(out_ids.cpu().numpy(), ids1)
+        assert np.array_equal(out_sc.cpu().numpy(), sc1)
+        g = gathered.cpu().numpy().view(CAND_DTYPE)
+        assert g["valid"].max() == 1
+    for sh in (one, a, b):
+        sh.close()
