@@ -213,6 +213,7 @@ class Shard:
 
     # ---- search
     def set_stream(self, stream_ptr):
+        """stream_ptr: a cudaStream_t as int (0/None = the legacy default stream, torch's default current stream)."""
         check(self._lib.b200rag_set_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None))
 
     def set_slack(self, slack: int):

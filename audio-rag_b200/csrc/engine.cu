@@ -282,7 +282,7 @@ int b200rag_set_stream(b200rag_shard* sp, void* stream) {
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
     B2_CUDA(cudaStreamSynchronize(s->stream));
-    s->stream = stream != nullptr ? (cudaStream_t)stream : s->own_stream;
+    s->stream = (cudaStream_t)stream;  // NULL == the legacy default stream
     return B200RAG_OK;
 }
 
@@ -574,7 +574,16 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
 
 int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
     if (sp == nullptr || out == nullptr) { set_error("get_stats: null argument"); return B200RAG_ERR_INVALID; }
-    *out = ((const Shard*)sp)->stats;
+    Shard* s = (Shard*)sp;
+    if (s->ws.post_count.p != nullptr && s->staged) {
+        // not on the timed path: read the postings counter the last sparse scan accumulated
+        unsigned long long v = 0;
+        if (cudaSetDevice(s->cfg.device) == cudaSuccess &&
+            cudaMemcpyAsync(&v, s->ws.post_count.p, 8, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+            cudaStreamSynchronize(s->stream) == cudaSuccess)
+            s->stats.sparse_postings = (int64_t)v;
+    }
+    *out = s->stats;
     return B200RAG_OK;
 }
 

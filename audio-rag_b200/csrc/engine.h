@@ -40,7 +40,8 @@ constexpr int kScanConsumerWarps = 8;
 constexpr int kScanTileRows = 16;
 constexpr int kSparseThreads = 512;
 constexpr int kMaxQueryTermsChunk = 256;
-constexpr int kMergeMaxKeys = 8192;
+constexpr int kMergeMaxKeys = 8192;    // smem bound of one merge group
+constexpr int kMergeGroupKeys = 1024;  // preferred group size (keeps the bitonic network short)
 
 struct DevPtr {
     void* p = nullptr;

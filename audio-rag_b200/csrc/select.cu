@@ -35,17 +35,23 @@ int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uin
                                      kMergeMaxKeys * 8));
         attr_set = true;
     }
+    // Many small groups per level instead of one big sort: a bitonic network over n keys costs
+    // ~log2(n)^2/2 barrier-separated stages, so groups are kept at <= kMergeGroupKeys keys and the tree
+    // gets an extra (cheap, parallel) level instead.
     uint64_t* cur = a;
     uint64_t* nxt = b;
     while (n_lists > 1) {
-        int lpg = kMergeMaxKeys / Lc;
+        int lpg = kMergeGroupKeys / Lc;
         if (lpg < 2) lpg = 2;
         if (lpg > n_lists) lpg = n_lists;
         const int n_groups = (n_lists + lpg - 1) / lpg;
         const int npow2 = next_pow2(lpg * Lc);
         if (npow2 > kMergeMaxKeys) { set_error("merge: candidate list too long"); return B200RAG_ERR_INVALID; }
+        int threads = npow2 / 2;
+        if (threads < 64) threads = 64;
+        if (threads > 512) threads = 512;
         dim3 grid(n_groups, batch);
-        merge_lists_kernel<<<grid, 512, (size_t)npow2 * 8, s->stream>>>(cur, n_lists, Lc, nxt, lpg, n_groups, npow2);
+        merge_lists_kernel<<<grid, threads, (size_t)npow2 * 8, s->stream>>>(cur, n_lists, Lc, nxt, lpg, n_groups, npow2);
         B2_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
         uint64_t* t = cur; cur = nxt; nxt = t;
@@ -59,43 +65,51 @@ int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uin
 __device__ __forceinline__ double bf16lo_d(uint32_t u) { return (double)__uint_as_float(u << 16); }
 __device__ __forceinline__ double bf16hi_d(uint32_t u) { return (double)__uint_as_float(u & 0xFFFF0000u); }
 
-__global__ void __launch_bounds__(128) rescore_dense_kernel(const uint16_t* __restrict__ corpus, int dim,
+// One warp per candidate.  Canonical order (oracle.py::dense_scores): lane l owns elements k with (k % 256) / 8 == l,
+// adds its exact fp64 products in ascending k, then the 32 lane partials are combined by a pairwise tree.
+__global__ void __launch_bounds__(256) rescore_dense_kernel(const uint16_t* __restrict__ corpus, int dim,
                                                             const uint16_t* __restrict__ q_bits,
                                                             const uint64_t* __restrict__ approx,
                                                             uint64_t* __restrict__ exact, int Lc) {
-    extern __shared__ __align__(16) double q64[];
-    const int q = blockIdx.x;
-    for (int k = threadIdx.x; k < dim; k += blockDim.x)
-        q64[k] = (double)__uint_as_float(((uint32_t)q_bits[(size_t)q * dim + k]) << 16);
-    __syncthreads();
-    for (int i = threadIdx.x; i < Lc; i += blockDim.x) {
-        const uint64_t key = approx[(size_t)q * Lc + i];
-        uint64_t ek = 0;
-        if (key != 0) {
-            const uint32_t row = key_row(key);
-            const uint4* rp = reinterpret_cast<const uint4*>(corpus + (size_t)row * dim);
-            double acc = 0.0;
-            for (int k8 = 0; k8 < dim / 8; ++k8) {
-                const uint4 v = rp[k8];
-                const double* qq = q64 + k8 * 8;
-                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.x), qq[0]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.x), qq[1]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.y), qq[2]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.y), qq[3]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.z), qq[4]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.z), qq[5]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(v.w), qq[6]));
-                acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(v.w), qq[7]));
-            }
-            ek = make_key(__double2float_rn(acc) + 0.0f, row);
-        }
-        exact[(size_t)q * Lc + i] = ek;
+    const int q = blockIdx.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + w;
+    if (i >= Lc) return;
+    const uint64_t key = approx[(size_t)q * Lc + i];
+    if (key == 0) {
+        if (lane == 0) exact[(size_t)q * Lc + i] = 0;
+        return;
     }
+    const uint32_t row = key_row(key);
+    const uint4* rp = reinterpret_cast<const uint4*>(corpus + (size_t)row * dim);
+    const uint4* qp = reinterpret_cast<const uint4*>(q_bits + (size_t)q * dim);
+    const int nch = dim / 256;
+    uint4 cv[4], qv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < nch) { cv[c] = rp[c * 32 + lane]; qv[c] = qp[c * 32 + lane]; }
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < nch) {
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].x), bf16lo_d(qv[c].x)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].x), bf16hi_d(qv[c].x)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].y), bf16lo_d(qv[c].y)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].y), bf16hi_d(qv[c].y)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].z), bf16lo_d(qv[c].z)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].z), bf16hi_d(qv[c].z)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].w), bf16lo_d(qv[c].w)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].w), bf16hi_d(qv[c].w)));
+        }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+    if (lane == 0) exact[(size_t)q * Lc + i] = make_key(__double2float_rn(acc) + 0.0f, row);
 }
 
 int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact) {
-    rescore_dense_kernel<<<batch, 128, (size_t)s->dim * 8, s->stream>>>(
-        s->dense.as<uint16_t>(), s->dim, s->ws.q_bits.as<uint16_t>(), approx, exact, Lc);
+    dim3 grid((Lc + 7) / 8, batch);
+    rescore_dense_kernel<<<grid, 256, 0, s->stream>>>(s->dense.as<uint16_t>(), s->dim,
+                                                      s->ws.q_bits.as<uint16_t>(), approx, exact, Lc);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;

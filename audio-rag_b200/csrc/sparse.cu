@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
     uint32_t* seg_s = reinterpret_cast<uint32_t*>(sel + kSelCap);
     uint32_t* seg_e = seg_s + kMaxQueryTermsChunk;
     float* qw = reinterpret_cast<float*>(seg_e + kMaxQueryTermsChunk);
+    uint32_t* seg_s_raw = reinterpret_cast<uint32_t*>(qw + kMaxQueryTermsChunk);
+    uint32_t* seg_e_raw = seg_s_raw + kMaxQueryTermsChunk;
+    float* qw_raw = reinterpret_cast<float*>(seg_e_raw + kMaxQueryTermsChunk);
     __shared__ int cnt_s;
     __shared__ unsigned long long npost_s;
 
@@ -71,26 +74,58 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
     const uint4* pd = reinterpret_cast<const uint4*>(p.post_doc);
     const float4* pw = reinterpret_cast<const float4*>(p.post_w);
 
+    __shared__ int nne_s;
     for (int64_t c0 = qs; c0 < qe; c0 += kMaxQueryTermsChunk) {
         const int cn = (int)min((int64_t)kMaxQueryTermsChunk, qe - c0);
         __syncthreads();
         for (int j = tid; j < cn; j += NT) {
             const uint32_t t = p.q_terms[c0 + j];
-            qw[j] = p.q_w[c0 + j];
+            qw_raw[j] = p.q_w[c0 + j];
             const uint32_t s = D[t], e = D[t + 1];
-            seg_s[j] = s;
-            seg_e[j] = e;
+            seg_s_raw[j] = s;
+            seg_e_raw[j] = e;
             if (e > s) atomicAdd(&npost_s, (unsigned long long)(e - s));
         }
         __syncthreads();
-        for (int j = 0; j < cn; ++j) {
-            const uint32_t s = seg_s[j], e = seg_e[j];
-            if (s == e) continue;  // uniform
+        // warp 0 compacts the terms that have postings in this block (order preserved: ascending term id)
+        if (tid < 32) {
+            int base_n = 0;
+            for (int j0 = 0; j0 < cn; j0 += 32) {
+                const int j = j0 + tid;
+                const bool ne = j < cn && seg_e_raw[j] > seg_s_raw[j];
+                const unsigned bal = __ballot_sync(0xffffffffu, ne);
+                if (ne) {
+                    const int pos = base_n + __popc(bal & ((1u << tid) - 1u));
+                    seg_s[pos] = seg_s_raw[j];
+                    seg_e[pos] = seg_e_raw[j];
+                    qw[pos] = qw_raw[j];
+                }
+                base_n += __popc(bal);
+            }
+            if (tid == 0) nne_s = base_n;
+        }
+        __syncthreads();
+        const int nne = nne_s;
+        // software pipeline: the first vector of term j+1 is in flight while term j is applied
+        uint4 nd4 = make_uint4(0, 0, 0, 0);
+        float4 nwa = make_float4(0, 0, 0, 0), nwb = nwa;
+        if (nne > 0) {
+            const int64_t P0 = base + seg_s[0], P1 = base + seg_e[0];
+            const int64_t vec = (P0 >> 3) + tid;
+            if ((vec << 3) < P1) { nd4 = pd[vec]; nwa = pw[2 * vec]; nwb = pw[2 * vec + 1]; }
+        }
+        for (int j = 0; j < nne; ++j) {
             const float wq = qw[j];
-            const int64_t P0 = base + s, P1 = base + e;
+            const int64_t P0 = base + seg_s[j], P1 = base + seg_e[j];
+            uint4 d4 = nd4;
+            float4 wa = nwa, wb = nwb;
+            if (j + 1 < nne) {
+                const int64_t Q0 = base + seg_s[j + 1], Q1 = base + seg_e[j + 1];
+                const int64_t nvec = (Q0 >> 3) + tid;
+                if ((nvec << 3) < Q1) { nd4 = pd[nvec]; nwa = pw[2 * nvec]; nwb = pw[2 * nvec + 1]; }
+            }
             for (int64_t vec = (P0 >> 3) + tid; (vec << 3) < P1; vec += NT) {
-                const uint4 d4 = pd[vec];
-                const float4 wa = pw[2 * vec], wb = pw[2 * vec + 1];
+                if (vec != (P0 >> 3) + tid) { d4 = pd[vec]; wa = pw[2 * vec]; wb = pw[2 * vec + 1]; }
                 const int64_t P = vec << 3;
                 const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
                 const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -180,7 +215,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
 
 template <int EPT>
 static int launch_scan_t(Shard* s, const SparseScanParams& p, int batch) {
-    const size_t smem = (size_t)EPT * kSparseThreads * 4 + (size_t)kSelCap * 8 + (size_t)kMaxQueryTermsChunk * 12;
+    const size_t smem = (size_t)EPT * kSparseThreads * 4 + (size_t)kSelCap * 8 + (size_t)kMaxQueryTermsChunk * 24;
     auto kern = sparse_scan_kernel<EPT>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)s->n_blocks, (unsigned)batch);

@@ -89,7 +89,9 @@ int b200rag_normalize_bf16(const float* x_host, int64_t n, int32_t dim, uint16_t
 /* ---- shard lifetime  (replaces QdrantClient(...) construction, qdrant.py:35-54) ------------------------ */
 int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out);
 void b200rag_shard_destroy(b200rag_shard* s);
-int b200rag_set_stream(b200rag_shard* s, void* cuda_stream); /* run on the caller's stream (NULL = own stream) */
+/* Run on the caller's cudaStream_t (NULL == the legacy default stream).  Until this is called the shard
+ * uses a private non-blocking stream. */
+int b200rag_set_stream(b200rag_shard* s, void* cuda_stream);
 int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximate candidates per leg before the
                                                                 exact re-score (0 = default max(16, L/2))      */
 int b200rag_sync(b200rag_shard* s);

@@ -69,22 +69,33 @@ def normalize_bf16(x):
 # ----------------------------------------------------------------------------- canonical leg scoring
 
 def dense_scores(corpus_bits, q_bits, rows=None):
-    """R2 canonical: score[r] = fp32( sum_k fp64(c[r,k]) * fp64(q[k]) ), k ascending, fp64 adds.
+    """R2 canonical dense score, fp64 accumulate in a fixed, documented order, then one cast to fp32.
 
-    A bf16*bf16 product is exact in fp64, so fused or unfused multiply-add give the same bits."""
+    Element k of a row belongs to lane l = (k % 256) // 8.  Lane partial p_l = sum of its products in
+    ascending k (fp64 adds, sequential); score = pairwise tree over the 32 lane partials
+    ((p0+p1)+(p2+p3))+... ; result fp32(score) + 0.0.  A bf16*bf16 product is exact in fp64, so fused
+    or unfused multiply-add give the same bits.  (dim must be a multiple of 256.)"""
     c = np.asarray(corpus_bits, dtype=np.uint16)
     if rows is not None:
         c = c[np.asarray(rows, dtype=np.int64)]
+    n, dim = c.shape
+    assert dim % 256 == 0
+    nch = dim // 256
     q = bf16_bits_to_f32(np.asarray(q_bits, dtype=np.uint16)).astype(np.float64)
-    acc = np.zeros(c.shape[0], dtype=np.float64)
-    blk = 65536
-    for s in range(0, c.shape[0], blk):
+    qv = q.reshape(nch, 32, 8).transpose(1, 0, 2).reshape(32, nch * 8)          # [lane, step]
+    out = np.empty(n, dtype=np.float32)
+    blk = 32768
+    for s in range(0, n, blk):
         cf = bf16_bits_to_f32(c[s:s + blk]).astype(np.float64)
-        a = np.zeros(cf.shape[0], dtype=np.float64)
-        for k in range(cf.shape[1]):
-            a += cf[:, k] * q[k]
-        acc[s:s + blk] = a
-    return (acc.astype(np.float32) + np.float32(0.0)).astype(np.float32)
+        m = cf.shape[0]
+        cv = cf.reshape(m, nch, 32, 8).transpose(0, 2, 1, 3).reshape(m, 32, nch * 8)
+        p = np.zeros((m, 32), dtype=np.float64)
+        for t in range(nch * 8):
+            p += cv[:, :, t] * qv[None, :, t]
+        while p.shape[1] > 1:
+            p = p[:, 0::2] + p[:, 1::2]
+        out[s:s + blk] = p[:, 0].astype(np.float32)
+    return (out + np.float32(0.0)).astype(np.float32)
 
 
 def check_sparse_vector(idx, val):

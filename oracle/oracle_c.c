@@ -4,7 +4,7 @@
  * third-party qdrant-client, absent here; the reference has no golden vectors for this path).
  *
  * Follows, rule by rule:
- *   R2  dense score  = fp32( sum_k fp64(c_k)*fp64(q_k) ), k ascending     (qdrant local/distances.py::cosine_similarity
+ *   R2  dense score  = fp32( fp64 sum of c_k*q_k in the lane-blocked order of oracle.py )  (qdrant local/distances.py::cosine_similarity
  *                                                                         on the unit vectors the engine stores as bf16)
  *   R3  sparse score = fp32( sum over common indices ascending of fp64(w_q)*fp64(w_d) )
  *                                                                        (local/sparse_distances.py::sparse_dot_product)
@@ -28,14 +28,27 @@ static inline double bf16_to_f64(uint16_t b) {
 }
 
 void oracle_dense_scores(const uint16_t* bits, int64_t n, int32_t dim, const uint16_t* q, float* out) {
+    /* canonical order of oracle.py::dense_scores: 32 lane partials (lane = (k % 256) / 8, ascending k),
+       then a pairwise tree over the lanes */
     double qd[4096];
+    const int nch = dim / 256;
     for (int k = 0; k < dim; ++k) qd[k] = bf16_to_f64(q[k]);
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < n; ++r) {
         const uint16_t* row = bits + r * (int64_t)dim;
-        double acc = 0.0;
-        for (int k = 0; k < dim; ++k) acc += bf16_to_f64(row[k]) * qd[k];
-        out[r] = (float)acc + 0.0f;
+        double p[32];
+        for (int l = 0; l < 32; ++l) {
+            double acc = 0.0;
+            for (int c = 0; c < nch; ++c)
+                for (int e = 0; e < 8; ++e) {
+                    const int k = c * 256 + l * 8 + e;
+                    acc += bf16_to_f64(row[k]) * qd[k];
+                }
+            p[l] = acc;
+        }
+        for (int w = 32; w > 1; w >>= 1)
+            for (int i = 0; i < w / 2; ++i) p[i] = p[2 * i] + p[2 * i + 1];
+        out[r] = (float)p[0] + 0.0f;
     }
 }
 
