@@ -49,7 +49,8 @@ class Query(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int32), ("dense_path", C.c_int32), ("dense_bytes", C.c_int64),
-                ("sparse_postings", C.c_int64), ("dense_passes", C.c_int32), ("retries", C.c_int32)]
+                ("sparse_postings", C.c_int64), ("dense_passes", C.c_int32), ("retries", C.c_int32),
+                ("dense_scan_ms", C.c_float), ("sparse_scan_ms", C.c_float)]
 
 
 # every symbol include/b200rag.h declares: (name, restype, argtypes)
@@ -78,8 +79,9 @@ SYMBOLS = [
     ("b200rag_stage", C.c_int, [_P, C.POINTER(Query)]),
     ("b200rag_legs_len", C.c_int, [C.POINTER(Query), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b200rag_legs", C.c_int, [_P, _P, _P]),
-    ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
+    ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     ("b200rag_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("b200rag_set_profiling", C.c_int, [_P, C.c_int32]),
     ("b200rag_synth_dense", C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P]),
     ("b200rag_synth_sparse", C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, C.c_int64,
                                        _P, _P, _P, _P]),
@@ -275,9 +277,12 @@ class Shard:
     def legs(self, cands_dev, ambiguous_dev=None):
         check(self._lib.b200rag_legs(self._h, _ptr(cands_dev), _ptr(ambiguous_dev)))
 
-    def fuse(self, gathered_dev, n_shards, out_ids_dev, out_scores_dev, out_counts_dev):
-        check(self._lib.b200rag_fuse(self._h, _ptr(gathered_dev), n_shards, _ptr(out_ids_dev), _ptr(out_scores_dev),
-                                     _ptr(out_counts_dev)))
+    def fuse(self, gathered_dev, n_shards, out_ids_dev, out_scores_dev, out_counts_dev, has_trailer=False):
+        check(self._lib.b200rag_fuse(self._h, _ptr(gathered_dev), n_shards, 1 if has_trailer else 0, _ptr(out_ids_dev),
+                                     _ptr(out_scores_dev), _ptr(out_counts_dev)))
+
+    def set_profiling(self, on: bool):
+        check(self._lib.b200rag_set_profiling(self._h, 1 if on else 0))
 
     def stats(self) -> dict:
         st = Stats()

@@ -1,0 +1,120 @@
+"""Row-sharded search: one process per GPU, `torch.distributed` for the plumbing (NCCL over NVLink on GPUs).
+
+The path shards naturally: rows are independent in both legs, so rank r holds the contiguous row
+range [base_r, base_r + n_r) as its own `Shard` (global id = row_base + local) and answers every query for its
+rows.  The ONE exchange step is an all-gather of the per-shard candidate lists (already exact-scored and ordered
+under R5): [nlegs, B, L] 16-byte candidates + one trailer per rank, <= 1.6 MB per rank at B = 1024, L = 200 and
+656 bytes at B = 1, L = 20.  Every rank then runs the same merge + RRF kernel on the gathered buffer, so the
+fused result is identical on all ranks and bit-identical to a single-shard search (RRF needs GLOBAL ranks, so it
+runs after the gather, never per shard).
+
+torch is plumbing only: it owns the exchange buffers and the process group; all compute is `libb200rag.so`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._ffi import Shard
+
+
+def shard_bounds(n_total: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous row range of `rank` (balanced; starts aligned to `align` rows)."""
+    per = -(-n_total // world)
+    per = -(-per // align) * align
+    lo = min(n_total, rank * per)
+    hi = min(n_total, lo + per)
+    return lo, hi
+
+
+class ShardedSearcher:
+    """One rank's end of a sharded corpus.  `shard` is this rank's `Shard` (or a duck-typed double in CPU tests)."""
+
+    def __init__(self, shard, device: torch.device, group=None):
+        self.shard = shard
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._bufs: dict = {}
+
+    def _buffers(self, nlegs, B, L, k):
+        key = (nlegs, B, L, k)
+        b = self._bufs.get(key)
+        if b is None:
+            n = nlegs * B * L + 1                              # + trailer (ambiguity counter)
+            b = {
+                "mine": torch.zeros((n, 2), dtype=torch.int64, device=self.device),
+                "all": torch.zeros((self.world, n, 2), dtype=torch.int64, device=self.device),
+                # ids | scores(f64 bits) | counts(+flag) in ONE buffer -> one D2H per batch
+                "out": torch.zeros(2 * B * k + (B + 2) // 2 + 1, dtype=torch.int64, device=self.device),
+            }
+            b["host"] = torch.empty_like(b["out"], device="cpu")
+            if self.device.type == "cuda":
+                b["host"] = b["host"].pin_memory()
+            self._bufs[key] = b
+        return b
+
+    def broadcast_query(self, arrays: dict | None, src: int = 0) -> dict:
+        """Replicate a query batch from `src` (serving: the rank that received the request) to all ranks."""
+        if self.world == 1:
+            return arrays
+        obj = [arrays if self.rank == src else None]
+        dist.broadcast_object_list(obj, src=src, group=self.group)
+        return obj[0]
+
+    def stage(self, mode, top_k, q_bits=None, sp_indptr=None, sp_terms=None, sp_weights=None, mask_ids=None,
+              score_threshold=None, rrf_k=0):
+        q, keep = self.shard.make_query(mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids,
+                                        score_threshold, rrf_k)
+        self.shard.stage(q, keep)
+        nlegs, L = Shard.legs_len(q)
+        self._cur = (nlegs, q.batch, L, top_k)
+        return self._cur
+
+    def run_staged(self):
+        """legs -> all-gather -> fuse on the device; results stay in the device out buffer (no host sync)."""
+        nlegs, B, L, k = self._cur
+        b = self._buffers(nlegs, B, L, k)
+        mine, allb, out = b["mine"], b["all"], b["out"]
+        mine[-1].zero_()
+        self.shard.legs(mine, mine[-1])
+        if self.world > 1:
+            # output as the concatenation along dim 0 (the layout both NCCL and gloo accept)
+            dist.all_gather_into_tensor(allb.view(-1, 2), mine, group=self.group)
+            src = allb
+        else:
+            src = mine
+        self.shard.fuse(src, self.world, out[:B * k], out[B * k:2 * B * k], out[2 * B * k:], has_trailer=True)
+        return b
+
+    def fetch(self, b):
+        """Device -> pinned host read-back of the fused results: (ids [B,k], scores [B,k] f64, counts [B], ambiguous)."""
+        nlegs, B, L, k = self._cur
+        b["host"].copy_(b["out"], non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        h = b["host"].numpy()
+        ids = h[:B * k].reshape(B, k).copy()
+        scores = h[B * k:2 * B * k].view(np.float64).reshape(B, k).copy()
+        cnt = h[2 * B * k:].view(np.int32)
+        return ids, scores, cnt[:B].copy(), int(cnt[B])
+
+    def search(self, mode, top_k, q_bits=None, sp_indptr=None, sp_terms=None, sp_weights=None, mask_ids=None,
+               score_threshold=None, rrf_k=0, max_retries=4):
+        """Whole sharded path with HOST buffers (query replicated on every rank).  Returns (ids, scores, counts)."""
+        nlegs, B, L, k = self.stage(mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids, score_threshold,
+                                    rrf_k)
+        slack0 = None
+        for attempt in range(max_retries + 1):
+            ids, scores, counts, amb = self.fetch(self.run_staged())
+            if amb == 0 or attempt == max_retries:
+                break
+            # some shard's slack guard failed: widen on every rank (same decision everywhere: amb is global)
+            slack0 = max(16, L // 2) if slack0 is None else slack0
+            slack0 = slack0 * 2 + L
+            self.shard.set_slack(min(slack0, 3 * 256 - L))
+        if slack0 is not None:
+            self.shard.set_slack(0)
+        return ids, scores, counts

@@ -246,6 +246,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     s->stats.dense_path = 1;
     s->stats.dense_passes = 0;
 
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
     int q = 0;
     while (q < batch) {
         int nq = (batch - q >= 2) ? 2 : 1;
@@ -295,6 +296,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         s->stats.dense_passes++;
         q += nq;
     }
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[1], s->stream)); s->ev_dense = true; }
     s->stats.dense_bytes = (int64_t)s->stats.dense_passes * s->n_rows * s->dim * 2;
     return B200RAG_OK;
 }

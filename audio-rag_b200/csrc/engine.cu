@@ -273,6 +273,8 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
     s->ws.exact.release(); s->ws.cands.release(); s->ws.out.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (int i = 0; i < 4; ++i)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -499,11 +501,12 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     if (!s->staged) { set_error("legs: no staged query batch"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
     s->stats = b200rag_stats{};
+    s->ev_dense = s->ev_sparse = false;
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
 
-int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int64_t* out_ids, double* out_scores,
-                 int32_t* out_counts) {
+int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int32_t has_trailer, int64_t* out_ids,
+                 double* out_scores, int32_t* out_counts) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || gathered == nullptr || n_shards < 1 || out_ids == nullptr || out_scores == nullptr || out_counts == nullptr) {
         set_error("fuse: bad argument");
@@ -513,7 +516,7 @@ int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int6
     B2_TRY(use_device(s));
     const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
     return launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
-                       out_ids, out_scores, out_counts);
+                       has_trailer, out_ids, out_scores, out_counts);
 }
 
 int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, double* out_scores,
@@ -549,7 +552,7 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
         }
         rc = run_legs(s, s->ws.cands.as<b200rag_cand>(), amb);
         if (rc != B200RAG_OK) break;
-        rc = launch_fuse(s, s->q.mode, B, L, K, s->q.rrf_k, s->ws.cands.as<b200rag_cand>(), 1, (int64_t*)(d + o_ids),
+        rc = launch_fuse(s, s->q.mode, B, L, K, s->q.rrf_k, s->ws.cands.as<b200rag_cand>(), 1, 0, (int64_t*)(d + o_ids),
                          (double*)(d + o_sc), (int32_t*)(d + o_cnt));
         if (rc != B200RAG_OK) break;
         cudaError_t e = cudaMemcpyAsync(hres, d, out_bytes, cudaMemcpyDeviceToHost, st);
@@ -583,7 +586,24 @@ int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
             cudaStreamSynchronize(s->stream) == cudaSuccess)
             s->stats.sparse_postings = (int64_t)v;
     }
+    if (s->profile && (s->ev_dense || s->ev_sparse) && cudaStreamSynchronize(s->stream) == cudaSuccess) {
+        float ms = 0.f;
+        if (s->ev_dense && cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) s->stats.dense_scan_ms = ms;
+        if (s->ev_sparse && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) s->stats.sparse_scan_ms = ms;
+        cudaGetLastError();
+    }
     *out = s->stats;
+    return B200RAG_OK;
+}
+
+int b200rag_set_profiling(b200rag_shard* sp, int32_t on) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    if (on && s->ev[0] == nullptr)
+        for (int i = 0; i < 4; ++i) B2_CUDA(cudaEventCreate(&s->ev[i]));
+    s->profile = on != 0;
+    s->ev_dense = s->ev_sparse = false;
     return B200RAG_OK;
 }
 

@@ -106,6 +106,9 @@ struct Shard {
 
     Workspace ws;
     b200rag_stats stats{};
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // dense scan begin/end, sparse scan begin/end
+    bool ev_dense = false, ev_sparse = false;
 
     // pinned host staging for results
     void* h_pinned = nullptr;
@@ -127,7 +130,7 @@ int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, u
 int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
                         float eps_abs, float eps_rel, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
-                int n_shards, int64_t* out_ids, double* out_scores, int32_t* out_counts);
+                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts);
 
 // ---- sparse.cu -----------------------------------------------------------------------------------------
 int build_inverted(Shard* s);

@@ -243,7 +243,8 @@ __device__ __forceinline__ bool cand_better(const b200rag_cand& f, const b200rag
 
 // smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
 __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
-                                                   int nlegs, int batch, int L, int top_k, int rrf_k,
+                                                   int64_t shard_stride, int has_trailer, int nlegs, int batch,
+                                                   int L, int top_k, int rrf_k,
                                                    int64_t* __restrict__ out_ids, double* __restrict__ out_scores,
                                                    int32_t* __restrict__ out_counts) {
     extern __shared__ __align__(16) uint8_t fsm[];
@@ -259,12 +260,18 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
     const int q = blockIdx.x;
     if (threadIdx.x < 2) leg_n[threadIdx.x] = 0;
     if (threadIdx.x == 0) total_s = 0;
+    if (has_trailer && q == 0 && threadIdx.x == 0) {
+        int amb = 0;
+        for (int sh = 0; sh < n_shards; ++sh)
+            amb += (int)(gathered[(size_t)sh * shard_stride + (size_t)nlegs * batch * L].id & 0xFFFFFFFFll);
+        out_counts[batch] = amb;
+    }
 
     for (int leg = 0; leg < nlegs; ++leg) {
         __syncthreads();
         for (int i = threadIdx.x; i < M; i += blockDim.x) {
             const int sh = i / L, j = i - sh * L;
-            stage[i] = gathered[(((size_t)sh * nlegs + leg) * batch + q) * L + j];
+            stage[i] = gathered[(size_t)sh * shard_stride + (((size_t)leg * batch + q) * L + j)];
         }
         __syncthreads();
         int local = 0;
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
 }
 
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
-                int n_shards, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
+                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
     const int nlegs = mode == B200RAG_HYBRID ? 2 : 1;
     const size_t M = (size_t)n_shards * L;
     const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
@@ -352,8 +359,9 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    fuse_kernel<<<batch, 256, smem, s->stream>>>(gathered, n_shards, nlegs, batch, L, top_k, rrf_k, out_ids,
-                                                 out_scores, out_counts);
+    const int64_t shard_stride = (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
+    fuse_kernel<<<batch, 256, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
+                                                 rrf_k, out_ids, out_scores, out_counts);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;

@@ -243,16 +243,19 @@ int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists) {
     p.n_blocks = (int)s->n_blocks;
     p.post_count = s->ws.post_count.as<unsigned long long>();
     if (Lc > kSelCap) { set_error("sparse_scan: top-k too large"); return B200RAG_ERR_INVALID; }
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[2], s->stream)); }
+    int rc;
     switch (s->R / kSparseThreads) {
-        case 2: return launch_scan_t<2>(s, p, batch);
-        case 4: return launch_scan_t<4>(s, p, batch);
-        case 8: return launch_scan_t<8>(s, p, batch);
-        case 16: return launch_scan_t<16>(s, p, batch);
-        case 32: return launch_scan_t<32>(s, p, batch);
-        case 64: return launch_scan_t<64>(s, p, batch);
+        case 2: rc = launch_scan_t<2>(s, p, batch); break;
+        case 4: rc = launch_scan_t<4>(s, p, batch); break;
+        case 8: rc = launch_scan_t<8>(s, p, batch); break;
+        case 16: rc = launch_scan_t<16>(s, p, batch); break;
+        case 32: rc = launch_scan_t<32>(s, p, batch); break;
+        case 64: rc = launch_scan_t<64>(s, p, batch); break;
+        default: set_error("sparse_scan: unsupported docs_per_block"); return B200RAG_ERR_INVALID;
     }
-    set_error("sparse_scan: unsupported docs_per_block");
-    return B200RAG_ERR_INVALID;
+    if (rc == B200RAG_OK && s->profile) { B2_CUDA(cudaEventRecord(s->ev[3], s->stream)); s->ev_sparse = true; }
+    return rc;
 }
 
 // ================================================================================================ builder

@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- hybrid top-10 queries/sec & p50 latency over a 10M x 1024-d corpus on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]                   # the reference-shaped CPU path
+
+One "step" = one batch of B queries through the whole hot path (dense scan + sparse scan + per-leg top-L + exact
+re-score + RRF + top-k).  The corpus is FIXED at --rows (default 10M) and row-sharded over the N ranks
+("scaling": "strong"); rank r generates its own row range on its GPU with the deterministic device generators.
+
+  value       queries/s with the query batch already resident in HBM: per-step CUDA events on the launching
+              stream bracket [legs -> all-gather -> fuse]; the next step's queries are staged between steps, untimed.
+              K steps are timed, the step times summed, the MAX over ranks taken.
+  e2e         the same metric through the host-buffer call a plugin makes (`b200rag_search` at N=1, else
+              `ShardedSearcher.search`): fp32 host query vectors + sparse CSR in pinned/pageable host memory ->
+              normalise -> H2D -> kernels -> (all-gather) -> D2H of ids/scores, wall clock, max over ranks.
+  roofline    the dominant kernel (dense_scan): algorithmic bytes (rows_on_this_rank * dim * 2 per launch) / its mean
+              launch duration, measured with CUDA events inside the timed region, / the measured HBM copy peak.
+  cpu_baseline / --impl reference
+              the oracle's reference-shaped port (oracle.RefShapedIndex: fp32 sgemv + argsort, a Python two-pointer
+              loop per document, dict RRF -- the algorithmic shape of qdrant-client local mode, which the reference
+              runs with qdrant_in_memory=True) on a bounded row sample, scaled linearly to the full corpus.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "audio-rag_b200")]
+
+import numpy as np  # noqa: E402
+
+SEED, QSEED = 1234, 2000
+METRIC = "hybrid top-10 queries/sec, 10Mx1024-d corpus"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--top-k", type=int, default=10)
+    ap.add_argument("--mode", default="hybrid", choices=["dense", "sparse", "hybrid"])
+    ap.add_argument("--query-tokens", type=int, default=12)
+    ap.add_argument("--cpu-sample-rows", type=int, default=20_000)
+    ap.add_argument("--cpu-queries", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a):
+    return {"workload": f"{a.mode} dense(1024-d bf16 cosine)+sparse(Zipf BM25 impacts) RRF top-{a.top_k}, "
+                        f"{a.rows} synthetic 256-token chunks, query batch {a.batch}",
+            "corpus_rows": a.rows, "dim": a.dim, "batch": a.batch, "top_k": a.top_k, "search_type": a.mode,
+            "query_terms": a.query_tokens, "vocab": 250_002}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(a, steps, warmup, sample_rows):
+    """Reference-shaped CPU path on a bounded sample; returns (qps_at_full_rows, detail dict)."""
+    from b200rag import synth
+    from oracle import fast, oracle
+    n = min(sample_rows, a.rows)
+    dense = synth.bf16_bits_to_f32(fast.synth_dense_bf16(SEED, 0, n, a.dim))      # fp32 unit rows, like qdrant-local
+    thr = synth.zipf_thresholds(synth.VOCAB)
+    idf, tff = synth.bm25_tables(a.rows)
+    ip, tt, ww = fast.synth_sparse_csr(SEED, 0, n, thr, idf, tff, synth.VOCAB, 256, synth.TERM_PERM_MUL)
+    ref = oracle.RefShapedIndex(dense, ip, tt, ww)
+    nq = warmup + steps
+    qf = synth.dense_queries_f32(QSEED, 0, nq, n, a.dim, corpus_seed=SEED)
+    qi, qt, qw = synth.sparse_queries(QSEED, 0, nq, a.query_tokens, synth.VOCAB, thr)
+    times = []
+    for i in range(nq):
+        sl = slice(qi[i], qi[i + 1])
+        t0 = time.perf_counter()
+        if a.mode == "hybrid":
+            ref.hybrid(qf[i], qt[sl], qw[sl], None, a.top_k)
+        elif a.mode == "dense":
+            ref.dense_leg(qf[i], None, a.top_k)
+        else:
+            ref.sparse_leg(qt[sl], qw[sl], None, a.top_k)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_query_sample = float(np.mean(times))
+    scale = a.rows / n
+    qps = 1.0 / (per_query_sample * scale)
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = os.cpu_count()
+    detail = {"value": qps, "unit": "queries/s", "cores": int(blas_threads), "kind": "port",
+              "sample": f"{len(times)} single hybrid queries over a {n}-row slice of the corpus "
+                        f"({per_query_sample * 1e3:.1f} ms/query on the slice; BLAS sgemv uses {blas_threads} threads, "
+                        f"the per-document sparse loop is single-threaded Python as in qdrant-client local mode), "
+                        f"scaled x{scale:.0f} linearly to {a.rows} rows",
+              "p50_ms_on_sample": float(np.median(times) * 1e3), "host_cpus": os.cpu_count()}
+    return qps, detail, per_query_sample * scale * 1e3
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, detail, ms = cpu_reference(a, a.steps, a.warmup, a.cpu_sample_rows)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms * a.batch, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),
+            "cpu_baseline": detail,
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_uuid):
+        self.rows, self.proc, self.uuid = [], None, gpu_uuid
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- the CUDA arm
+def build_shard(a, dev, lo, hi):
+    import torch
+    from b200rag import Shard, synth
+    n = hi - lo
+    sparse = a.mode != "dense"
+    sh = Shard(dim=a.dim, device=dev.index, row_base=lo, reserve_rows=n, reserve_postings=int(n * 198) if sparse else 0)
+    sh.set_stream(torch.cuda.current_stream().cuda_stream)
+    thr = torch.from_numpy(synth.zipf_thresholds(synth.VOCAB).view(np.int64)).to(dev)
+    idf_h, tff_h = synth.bm25_tables(a.rows)
+    idf, tff = torch.from_numpy(idf_h).to(dev), torch.from_numpy(tff_h).to(dev)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        bits = torch.empty((m, a.dim), dtype=torch.int16, device=dev)
+        sh.synth_dense(SEED, lo + s, m, bits)
+        if sparse:
+            counts = torch.empty(m, dtype=torch.int64, device=dev)
+            sh.synth_sparse(SEED, lo + s, m, 256, thr, idf, tff, synth.TERM_PERM_MUL, counts, None, None, None)
+            indptr = torch.empty(m + 1, dtype=torch.int64, device=dev)
+            sh.exclusive_scan_i64(counts, m, indptr)
+            nnz = int(indptr[-1].item())
+            terms = torch.empty(nnz, dtype=torch.int32, device=dev)
+            w = torch.empty(nnz, dtype=torch.float32, device=dev)
+            sh.synth_sparse(SEED, lo + s, m, 256, thr, idf, tff, synth.TERM_PERM_MUL, None, indptr, terms, w)
+            sh.add_device(m, bits, indptr, terms, w, nnz)
+            del counts, indptr, terms, w
+        else:
+            sh.add_device(m, bits)
+        del bits
+    if sparse:
+        sh.build()
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    return sh
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from b200rag import _ffi, normalize_bf16, synth
+    from b200rag.dist import ShardedSearcher, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if _ffi.device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 device visible; this path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+
+    lo, hi = shard_bounds(a.rows, world, rank, align=8192)
+    t_build = time.time()
+    sh = build_shard(a, dev, lo, hi)
+    t_build = time.time() - t_build
+    ss = ShardedSearcher(sh, dev)
+    B, K, W = a.batch, a.steps, a.warmup
+    nsteps = W + K
+
+    # host-side queries for every step (fp32 unit vectors + sparse CSR: what an embedder hands the plugin)
+    thr_h = synth.zipf_thresholds(synth.VOCAB)
+    qf = synth.dense_queries_f32(QSEED, 0, nsteps * B, a.rows, a.dim, corpus_seed=SEED)
+    qi, qt, qw = synth.sparse_queries(QSEED, 0, nsteps * B, a.query_tokens, synth.VOCAB, thr_h)
+
+    def step_arrays(i):
+        s, e = i * B, (i + 1) * B
+        return qf[s:e], (qi[s:e + 1] - qi[s]), qt[qi[s]:qi[e]], qw[qi[s]:qi[e]]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(str(torch.cuda.get_device_properties(dev).uuid))
+        if not sampler.uuid.startswith("GPU-"):
+            sampler.uuid = "GPU-" + sampler.uuid
+
+    # ------------------------------------------------------------------ (1) device-resident timing -> value
+    sh.set_profiling(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    dense_ms, sparse_ms, launches, dense_bytes, postings = [], [], 0, 0, 0
+    barrier()
+    if sampler:
+        sampler.start()
+    wall0 = None
+    for i in range(nsteps):
+        f, ip, tt, ww = step_arrays(i)
+        ss.stage(a.mode, a.top_k, normalize_bf16(f), ip, tt, ww)          # untimed: inputs resident before the step
+        if i == W:
+            barrier()
+            wall0 = time.perf_counter()
+        if i >= W:
+            ev[i - W][0].record()
+        b = ss.run_staged()
+        if i >= W:
+            ev[i - W][1].record()
+            st = sh.stats()                                               # syncs; outside the event bracket
+            dense_ms.append(st["dense_scan_ms"]); sparse_ms.append(st["sparse_scan_ms"])
+            launches += st["kernel_launches"] + 1 + (1 if world > 1 else 0)   # + trailer memset (+ NCCL kernel)
+            dense_bytes, postings = st["dense_bytes"], st["sparse_postings"]
+    barrier()
+    wall_value = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = np.array([s.elapsed_time(e) for s, e in ev], dtype=np.float64)
+    total_ms = float(step_ms.sum())
+    ids_dev, sc_dev, cnt_dev, amb = ss.fetch(b)
+    sh.set_profiling(False)
+
+    # ------------------------------------------------------------------ (2) end-to-end through the host-buffer call
+    e2e_t = []
+    h2d = B * a.dim * 2 + (B + 1) * 8 + 0 + B * 8
+    barrier()
+    for i in range(nsteps):
+        f, ip, tt, ww = step_arrays(i)
+        if i == W:
+            barrier()
+        t0 = time.perf_counter()
+        qb = normalize_bf16(f)
+        if world == 1:
+            r_ids, r_sc, r_cnt = sh.search(a.mode, a.top_k, qb, ip, tt, ww)
+        else:
+            r_ids, r_sc, r_cnt = ss.search(a.mode, a.top_k, qb, ip, tt, ww)
+        if i >= W:
+            e2e_t.append(time.perf_counter() - t0)
+            h2d = max(h2d, B * a.dim * 2 + (B + 1) * 8 + len(tt) * 8 + B * 8)
+    barrier()
+    e2e_total = float(np.sum(e2e_t))
+    d2h = B * a.top_k * 16 + (B + 1) * 4
+    # the last e2e step and the last device-resident step used the same queries: results must agree
+    same = bool(np.array_equal(r_ids, ids_dev) and np.array_equal(r_sc, sc_dev))
+
+    # ------------------------------------------------------------------ reduce over ranks (MAX)
+    red = torch.tensor([total_ms, e2e_total, float(np.mean(dense_ms)), float(np.mean(sparse_ms)), wall_value],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total, dense_k_ms, sparse_k_ms, wall_value = [float(x) for x in red.tolist()]
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"dense_scan_rows_{hi - lo}")
+            except Exception:
+                traffic = None
+        rows_rank = hi - lo
+        algo_gb = rows_rank * a.dim * 2 / 1e9
+        achieved = algo_gb / (dense_k_ms / 1e3) if dense_k_ms > 0 else 0.0
+        qps = B * K / (total_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {**workload(a), "rows_per_gpu": rows_rank,
+                       "parallelism": f"row-sharded x{world}, one process per GPU, NCCL all-gather of per-shard "
+                                      f"candidates + merge/RRF kernel on every rank",
+                       "l2": f"inputs larger than L2: {algo_gb:.2f} GB of corpus rows per GPU per step vs 126 MB L2; "
+                             f"a different query every step",
+                       "timing": "CUDA events per step on the launching stream, summed over K steps, max over ranks"},
+            "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),
+            "wall_ms_per_step_incl_staging": wall_value / K * 1e3,
+            "e2e": {"value": B * K / e2e_total, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "p50_ms": float(np.median(e2e_t) * 1e3),
+                    "api": "b200rag_search (C ABI, host buffers)" if world == 1 else
+                           "b200rag.dist.ShardedSearcher.search (host buffers; stage/legs/fuse C ABI + NCCL all-gather)",
+                    "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                         "algorithmic_bytes_per_launch": int(rows_rank * a.dim * 2),
+                         "kernel_ms": dense_k_ms, "kernel_share_of_step": dense_k_ms / (total_ms / K),
+                         "sparse_scan_ms": sparse_k_ms, "sparse_postings_per_step": int(postings),
+                         "step_algorithmic_GBps": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3),
+                         "step_frac": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3) / peak},
+            "clocks": clocks,
+            "build_s": t_build, "ambiguous_flags": int(amb),
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                _, detail, _ = cpu_reference(a, a.cpu_queries, 2, a.cpu_sample_rows)
+                line["cpu_baseline"] = detail
+            except Exception as e:  # the oracle is a checker, never a dependency of the measured path
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -132,12 +132,16 @@ int b200rag_search(b200rag_shard* s, const b200rag_query* q, int64_t* out_ids_ho
  *           nlegs = 2 (dense, sparse) for HYBRID else 1, L = 2*top_k for HYBRID else top_k;
  *           ambiguous_dev (device int32, may be NULL) is incremented when a leg's slack guard fails;
  *   fuse  : merge `n_shards` gathered candidate sets [n_shards, nlegs, batch, L] under R5, then RRF under
- *           R9/R10 (HYBRID), writing device results [batch, top_k]. */
+ *           R9/R10 (HYBRID), writing device results [batch, top_k].
+ * Exchange format: with has_trailer != 0 every shard's block is followed by ONE trailer b200rag_cand whose
+ * `id` low word is that shard's ambiguity counter (pass &trailer as ambiguous_dev to b200rag_legs), i.e. the
+ * gathered buffer is [n_shards, nlegs*batch*L + 1]; fuse then also writes the sum of the counters to
+ * out_counts_dev[batch] (so out_counts_dev holds batch + 1 ints). */
 int b200rag_stage(b200rag_shard* s, const b200rag_query* q);
 int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L);
 int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
-int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int64_t* out_ids_dev,
-                 double* out_scores_dev, int32_t* out_counts_dev);
+int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int32_t has_trailer,
+                 int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
 
 /* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
 typedef struct {
@@ -147,8 +151,12 @@ typedef struct {
     int64_t sparse_postings;     /* postings of the query terms in this shard (sum over batch)            */
     int32_t dense_passes;        /* corpus passes made for the batch                                      */
     int32_t retries;             /* slack-guard retries inside b200rag_search                              */
+    float dense_scan_ms;         /* with profiling on: device time of the dense scan kernel(s) of the last legs */
+    float sparse_scan_ms;        /* ... and of the sparse scan kernel (CUDA events on the shard's stream)      */
 } b200rag_stats;
 int b200rag_get_stats(const b200rag_shard* s, b200rag_stats* out);
+/* Bracket the two scan kernels with CUDA events on the launching stream (bench.py's roofline figures). */
+int b200rag_set_profiling(b200rag_shard* s, int32_t on);
 
 /* ---- synthetic corpus generation on the device (bench / tests; twins of b200rag/synth.py) -------------- */
 int b200rag_synth_dense(b200rag_shard* s, uint64_t seed, int64_t global_row_start, int64_t n, uint16_t* out_bits_dev);

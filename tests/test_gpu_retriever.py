@@ -1,0 +1,78 @@
+"""B200Retriever on a real B200: against the committed golden fixture (expected outputs of the reference's own
+plugin code, tests/make_golden.py) and against its oracle-backed twin through the same adapter code."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from data_small import DIM, make_chunks, make_queries, result_rows
+from oracle_shard import OracleShard
+
+pytestmark = pytest.mark.gpu
+
+
+def _types():
+    from b200rag.compat import AudioChunk, EmbeddingResult, SparseVector
+    return AudioChunk, EmbeddingResult, SparseVector
+
+
+def _retriever(gpu, **cfg):
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever
+    try:
+        conf = RetrievalConfig(qdrant_in_memory=True, **cfg)
+    except TypeError:
+        conf = RetrievalConfig(**cfg)
+    return B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024)
+
+
+def test_golden_fixture(gpu):
+    import make_golden
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "retrieval_golden.json")))
+    assert gold["dim"] == DIM
+    r = _retriever(gpu)
+    make_golden.load(r, _types())
+    got = make_golden.run_cases(r, _types())
+    assert len(got) == len(gold["cases"])
+    for g, e in zip(got, gold["cases"]):
+        assert g == e, f"case {e['search_type']} k={e['top_k']} {e['collection']} {e['filter']} q{e['query']}"
+    assert r._shard is not None and type(r._shard).__name__ == "Shard"
+    r.close()
+
+
+def test_adapter_gpu_vs_oracle_twin(gpu):
+    A, E, S = _types()
+    real, twin = _retriever(gpu, top_k=6), _retriever(gpu, top_k=6)
+    twin._shard = OracleShard(dim=DIM)
+    data = {"t1": make_chunks(700, 41, "T1", A, E, S), "t2": make_chunks(300, 42, "T2", A, E, S),
+            "old": make_chunks(200, 43, "O", A, E, S, sparse=False)}
+    for name, (ch, em) in data.items():
+        for s in range(0, len(ch), 170):
+            real.add(ch[s:s + 170], em[s:s + 170], name)
+            twin.add(ch[s:s + 170], em[s:s + 170], name)
+    qs = make_queries(6, 51, 700, 41, E, S)
+    for st in ("dense", "sparse", "hybrid"):
+        for name in list(data) + ["unknown"]:
+            for flt in (None, {"lang": "en"}):
+                for q in qs[:3]:
+                    a = result_rows(real.search(q, collection_name=name, search_type=st, filter_metadata=flt))
+                    b = result_rows(twin.search(q, collection_name=name, search_type=st, filter_metadata=flt))
+                    assert a == b, (st, name, flt)
+    # batched, mixed tenants in one call (config-4 style: one pass, one mask per query)
+    names = ["t1", "t2", "t1", "old", "t2", "t1"]
+    a = real.search_batch(qs, top_k=10, collection_name=names, search_type="hybrid")
+    b = twin.search_batch(qs, top_k=10, collection_name=names, search_type="hybrid")
+    assert [result_rows(x) for x in a] == [result_rows(x) for x in b]
+    # delete + re-add keeps parity
+    real.delete_collection("t1"); twin.delete_collection("t1")
+    ch, em = make_chunks(50, 44, "T1b", A, E, S)
+    real.add(ch, em, "t1"); twin.add(ch, em, "t1")
+    for q in qs[:2]:
+        for name in ("t1", "t2"):
+            assert result_rows(real.search(q, collection_name=name)) == result_rows(twin.search(q, collection_name=name))
+    assert real.count("t1") == 50 and real.count("t2") == 300
+    for name in ("t1", "t2", "old"):
+        real.delete_collection(name)
+    assert real._shard.count == 0
+    real.close()

@@ -1,0 +1,147 @@
+"""Host logic of B200Retriever (no GPU): the same requests as the reference's own QdrantRetriever builds, the same
+results as the reference's plugin code produces when its qdrant_client is the oracle-backed test double.
+Skipped where /root/reference is absent (GPU box); the golden fixture carries the expectations there."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import conftest
+from data_small import DIM, make_chunks, make_queries, result_rows
+from oracle_shard import OracleShard
+
+pytestmark = pytest.mark.skipif(not conftest.HAVE_REFERENCE, reason="reference checkout not present")
+
+
+def _pair(**cfg):
+    from audio_rag.config import RetrievalConfig
+    from audio_rag.retrieval import RetrievalRegistry
+    from b200rag.retriever import B200Retriever
+    conf = RetrievalConfig(qdrant_in_memory=True, **cfg)
+    ref = RetrievalRegistry.create("qdrant", config=conf, embedding_dim=DIM)
+    ours = RetrievalRegistry.create("b200", config=conf, embedding_dim=DIM)
+    assert isinstance(ours, B200Retriever)
+    ours._shard = OracleShard(dim=DIM)
+    return ref, ours
+
+
+def _types():
+    from audio_rag.core import AudioChunk, EmbeddingResult, SparseVector
+    return AudioChunk, EmbeddingResult, SparseVector
+
+
+def test_registry_and_types():
+    from audio_rag.core import BaseRetriever
+    from audio_rag.retrieval import RetrievalRegistry
+    from b200rag import compat
+    from b200rag.retriever import B200Retriever
+    assert compat.HAVE_REFERENCE and issubclass(B200Retriever, BaseRetriever)
+    assert "b200" in RetrievalRegistry and RetrievalRegistry.get("b200") is B200Retriever
+
+
+@pytest.mark.parametrize("coll_sparse", [True, False])
+@pytest.mark.parametrize("query_sparse", [True, False])
+@pytest.mark.parametrize("search_type", ["dense", "sparse", "hybrid", None])
+@pytest.mark.parametrize("threshold", [0.0, 0.3])
+def test_plan_matches_reference_request(coll_sparse, query_sparse, search_type, threshold):
+    """Branch/fallback/limits (R8, R11): compare our plan with the request the reference sends to qdrant."""
+    A, E, S = _types()
+    ref, ours = _pair(score_threshold=threshold, top_k=7)
+    chunks, embs = make_chunks(30, 1, "c", A, E, S, sparse=coll_sparse)
+    ref.add(chunks, embs, "col")
+    ours.add(chunks, embs, "col")
+    q = make_queries(1, 5, 30, 1, E, S, sparse=query_sparse)[0]
+    for top_k in (None, 3):
+        for flt in (None, {"lang": "en"}):
+            ref._get_client().requests.clear()
+            ref.search(q, top_k=top_k, collection_name="col", filter_metadata=flt, search_type=search_type)
+            req = ref._get_client().requests[-1]
+            plan = ours._plan_search(q, top_k, "col", flt, search_type)
+            assert plan["top_k"] == req["limit"]
+            assert plan["mode"] == {"fusion": "hybrid", "sparse": "sparse", "dense": "dense"}[req["query_kind"]]
+            if req["fusion"]:
+                assert [l for _, l in req["prefetch"]] == [plan["leg_limit"]] * 2 == [2 * plan["top_k"]] * 2
+                assert [u for u, _ in req["prefetch"]] == ["dense", "sparse"]
+            assert plan["score_threshold"] == req["score_threshold"]
+            assert (plan["filter"] or None) == (None if req["filter"] is None else
+                                                {k[len("metadata."):]: v for k, v in req["filter"].items()})
+
+
+def _compare_all(ref, ours, queries, names, **kw):
+    for q in queries:
+        for name in names:
+            a = result_rows(ref.search(q, collection_name=name, **kw))
+            b = result_rows(ours.search(q, collection_name=name, **kw))
+            assert a == b, f"{name} {kw}\n ref {a[:3]}\n our {b[:3]}"
+
+
+def test_results_match_reference_plugin_multi_collection():
+    A, E, S = _types()
+    ref, ours = _pair(top_k=5)
+    data = {"tenant_a": make_chunks(120, 11, "A", A, E, S), "tenant_b": make_chunks(80, 12, "B", A, E, S),
+            "legacy": make_chunks(60, 13, "L", A, E, S, sparse=False)}
+    # interleaved adds: the global row space mixes the tenants
+    for part in range(2):
+        for name, (ch, em) in data.items():
+            h = len(ch) // 2
+            sl = slice(0, h) if part == 0 else slice(h, None)
+            ref.add(ch[sl], em[sl], name)
+            ours.add(ch[sl], em[sl], name)
+    for name in data:
+        assert ref.count(name) == ours.count(name) == len(data[name][0])
+        assert ref.collection_exists(name) and ours.collection_exists(name)
+        assert ref.is_hybrid_collection(name) == ours.is_hybrid_collection(name)
+    qs = make_queries(4, 21, 120, 11, E, S) + make_queries(2, 22, 60, 13, E, S, sparse=False)
+    for st in ("dense", "sparse", "hybrid"):
+        _compare_all(ref, ours, qs, list(data), search_type=st)
+        _compare_all(ref, ours, qs[:2], list(data), search_type=st, top_k=17)
+    for flt in ({"lang": "de"}, {"source": "A-1.wav", "lang": "en"}, {"tags": "a"}, {"missing": 1}, {"idx": 4}):
+        _compare_all(ref, ours, qs[:3], ["tenant_a", "legacy"], search_type="hybrid", filter_metadata=flt)
+    # unknown collection: created empty, returns [] (R11), then counts 0
+    assert ref.search(qs[0], collection_name="nope") == ours.search(qs[0], collection_name="nope") == []
+    assert ref.count("nope") == ours.count("nope") == 0 and ours.collection_exists("nope")
+    # delete one tenant: the others are unaffected, the name can be reused
+    ref.delete_collection("tenant_a")
+    ours.delete_collection("tenant_a")
+    assert not ours.collection_exists("tenant_a")
+    _compare_all(ref, ours, qs[:2], ["tenant_b", "legacy"], search_type="hybrid")
+    ch, em = make_chunks(25, 14, "A2", A, E, S)
+    ref.add(ch, em, "tenant_a")
+    ours.add(ch, em, "tenant_a")
+    _compare_all(ref, ours, qs[:2], ["tenant_a", "tenant_b"], search_type="hybrid")
+    assert ref.count("tenant_a") == ours.count("tenant_a") == 25
+
+
+def test_default_collection_threshold_and_batch():
+    A, E, S = _types()
+    ref, ours = _pair(score_threshold=0.2, top_k=4, search_type="dense", collection_name="dflt")
+    ch, em = make_chunks(90, 31, "D", A, E, S, sparse=False)
+    ref.add(ch, em)
+    ours.add(ch, em)
+    qs = make_queries(5, 32, 90, 31, E, S)
+    _compare_all(ref, ours, qs, [None])                   # legacy collection: threshold applies (qdrant.py:331)
+    assert ref.count() == ours.count() == 90
+    batch = ours.search_batch(qs, top_k=4)
+    assert [result_rows(b) for b in batch] == [result_rows(ref.search(q)) for q in qs]
+    # add() edge cases (qdrant.py:154-160)
+    from audio_rag.core import RetrievalError
+    ours.add([], [])
+    with pytest.raises(RetrievalError):
+        ours.add(ch[:2], em[:1])
+    with pytest.raises(RetrievalError):
+        ours.add(ch[:1], [E(dense=[0.0] * 3)])
+    with pytest.raises(RetrievalError):
+        ours.add(ch[:1], [E(dense=em[0].dense, sparse=S(indices=[1, 1], values=[1.0, 2.0]))], "h2")
+    # results are copies: mutating one does not leak into the store (reranker builds on result.chunk)
+    r1 = ours.search(qs[0])
+    r1[0].chunk.metadata["poison"] = True
+    assert "poison" not in ours.search(qs[0])[0].chunk.metadata
+
+
+def test_golden_fixture_is_current():
+    """tests/golden/retrieval_golden.json was produced by make_golden.py from the reference plugin + test double."""
+    import make_golden
+    path = os.path.join(os.path.dirname(__file__), "golden", "retrieval_golden.json")
+    assert os.path.exists(path), "run python tests/golden/make_golden.py"
+    assert json.load(open(path)) == json.loads(json.dumps(make_golden.generate()))
