@@ -64,6 +64,8 @@ SYMBOLS = [
     ("b200rag_shard_destroy", None, [_P]),
     ("b200rag_set_stream", C.c_int, [_P, _P]),
     ("b200rag_set_slack", C.c_int, [_P, C.c_int32]),
+    ("b200rag_set_dense_path", C.c_int, [_P, C.c_int32]),
+    ("b200rag_debug_dense_scores", C.c_int, [_P, _P]),
     ("b200rag_sync", C.c_int, [_P]),
     ("b200rag_add", C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     ("b200rag_add_device", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64]),
@@ -220,6 +222,13 @@ class Shard:
 
     def set_slack(self, slack: int):
         check(self._lib.b200rag_set_slack(self._h, slack))
+
+    def set_dense_path(self, path: int):
+        """0 = auto, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM."""
+        check(self._lib.b200rag_set_dense_path(self._h, path))
+
+    def debug_dense_scores(self, out_scores_dev):
+        check(self._lib.b200rag_debug_dense_scores(self._h, _ptr(out_scores_dev)))
 
     def sync(self):
         check(self._lib.b200rag_sync(self._h))

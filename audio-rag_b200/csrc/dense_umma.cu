@@ -1,0 +1,328 @@
+// K1b  dense_gemm: query-batch x corpus inner products on the 5th-gen tensor cores (tcgen05 + TMEM), corpus and
+// query tiles staged by TMA, top-k fused in the TMEM epilogue -- the score matrix never reaches HBM.
+//
+// Replaces the dense leg of client.query_points for BATCHES of queries (search_batch; reference call sites
+// src/audio_rag/retrieval/qdrant.py:285-288, 317-332 issue one query at a time).
+//
+// GEMM shape per CTA tile:  D[128 queries x 256 corpus rows] (fp32, TMEM) = Q[128 x K] * C[256 x K]^T,
+// both operands bf16 K-major in shared memory with the 128-byte swizzle, K = dim stepped 64 elements per
+// pipeline stage (16 KB of queries + 32 KB of corpus rows per stage, 4 stages), 4 x tcgen05.mma (K = 16) per stage.
+// Queries are the M dimension on purpose: TMEM lane i then holds query i, so ONE epilogue thread owns ONE query and
+// can keep that query's running top-Lc threshold in a register and its sorted candidate list privately (no atomics,
+// no CTA-wide compaction).  The list is a sorted array in global memory (L1/L2 resident, touched only on the rare
+// insertion); thresholds are shared grid-wide through a monotone atomicMax like in the SIMT scan.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over 256-row corpus tiles):
+//   warp 0  TMA producer   (one lane): cp.async.bulk.tensor.2d of the query k-block and the corpus k-block
+//   warp 1  MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit -> smem-empty / tmem-full
+//   warp 2  TMEM allocator (512 columns = two 256-column accumulator buffers, so the epilogue of tile i overlaps
+//                           the MMAs of tile i+1)
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, compare, insert
+//
+// Roofline: HBM for <= ~200 queries per pass (intensity = B flop/byte), tensor pipe above.
+// Algorithmic bytes per launch = n_rows * dim * 2.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace b200rag {
+
+constexpr int kGemmM = 128;        // queries per pass (TMEM lanes)
+constexpr int kGemmN = 256;        // corpus rows per tile (TMEM columns per accumulator buffer)
+constexpr int kGemmKB = 64;        // K elements per pipeline stage (128 bytes: one swizzle span)
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 256;
+constexpr uint32_t kStageABytes = kGemmM * kGemmKB * 2;   // 16 KB
+constexpr uint32_t kStageBBytes = kGemmN * kGemmKB * 2;   // 32 KB
+constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmParams {
+    int64_t n_rows;
+    int64_t n_tiles;
+    int dim;
+    int batch;                     // valid queries in this pass (<= 128)
+    const uint32_t* const* masks;  // device array [batch] of eligibility bitmaps (entries may be null) or nullptr
+    uint64_t* g_thr;               // [batch]
+    uint64_t* out;                 // [batch][grid][Lc]
+    int64_t out_q_stride;          // grid * Lc
+    int Lc;
+    float* dbg_scores;             // optional [batch][n_rows] raw approximate scores (tests)
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
+                            ((uint32_t)(kGemmM >> 4) << 24);
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                  const GemmParams p) {
+    extern __shared__ uint8_t gsm_raw[];
+    // 1024-byte alignment for the 128B-swizzled tiles
+    uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + (size_t)kGemmStages * kStageBytes);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* tfull = empty + kGemmStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.dim / kGemmKB;
+    const int64_t t0 = p.n_tiles * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+    const int64_t t1 = p.n_tiles * (int64_t)(blockIdx.x + 1) / (int64_t)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_c);
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_s, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1u);
+                    uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                    mbar_arrive_expect_tx(&full[st], kStageBytes);
+                    tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
+                    tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * kGemmN));
+                    if (++st == kGemmStages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int64_t t = t0; t < t1; ++t, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kGemmN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(gsm + (size_t)st * kStageBytes);
+                    const uint64_t da = make_sw128_desc(sa);
+                    const uint64_t db = make_sw128_desc(sa + kStageABytes);
+#pragma unroll
+                    for (int k = 0; k < kGemmKB / 16; ++k)
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[st]);             // frees the smem stage when these MMAs retire
+                    if (kb == nkb - 1) umma_commit(&tfull[buf]);
+                    if (++st == kGemmStages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------------------------ epilogue
+        const int quad = warp - 4;                       // == warp % 4: the TMEM lane quadrant this warp may read
+        const int qi = quad * 32 + lane;                 // my query
+        const bool active = qi < p.batch;
+        uint64_t* list = p.out + (size_t)(active ? qi : 0) * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+        const uint32_t* mask = (active && p.masks != nullptr) ? p.masks[qi] : nullptr;
+        if (active)
+            for (int i = 0; i < p.Lc; ++i) list[i] = 0;
+        int cnt = 0;
+        uint64_t thr = 0;
+        float thr_s = -INFINITY;
+        int it = 0;
+        for (int64_t t = t0; t < t1; ++t, ++it) {
+            const int buf = it & 1;
+            if (active) {
+                const uint64_t g = ld_volatile_u64(&p.g_thr[qi]);
+                if (g > thr) { thr = g; thr_s = key_score(g); }
+            }
+            mbar_wait(&tfull[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kGemmN);
+            for (int c = 0; c < kGemmN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                if (!active) continue;
+                const int64_t row0 = t * kGemmN + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]) + 0.0f;
+                    const int64_t row = row0 + j;
+                    if (p.dbg_scores != nullptr && row < p.n_rows) p.dbg_scores[(size_t)qi * p.n_rows + row] = s;
+                    if (s >= thr_s && row < p.n_rows) {
+                        const uint64_t key = make_key(s, (uint32_t)row);
+                        if (key > thr) {
+                            bool ok = true;
+                            if (mask != nullptr) ok = (mask[row >> 5] >> (row & 31)) & 1u;
+                            if (ok) {
+                                // sorted insert into my private list (descending)
+                                int i = cnt < p.Lc ? cnt : p.Lc - 1;
+                                while (i > 0 && list[i - 1] < key) { list[i] = list[i - 1]; --i; }
+                                list[i] = key;
+                                if (cnt < p.Lc) ++cnt;
+                                if (cnt == p.Lc) {
+                                    const uint64_t nt = list[p.Lc - 1];
+                                    if (nt > thr) {
+                                        thr = nt;
+                                        thr_s = key_score(nt);
+                                        atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[qi]),
+                                                  (unsigned long long)nt);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    // ---- teardown: everyone meets, then the allocating warp frees TMEM
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B200RAG_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmKB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return B200RAG_ERR_CUDA; }
+    return B200RAG_OK;
+}
+
+int dense_gemm_nlists(const Shard* s) { return s->sm_count; }
+
+int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores) {
+    const int64_t n_tiles = (s->n_rows + kGemmN - 1) / kGemmN;
+    int grid = s->sm_count;
+    if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
+    *nlists = grid;
+    const size_t smem = (size_t)kGemmStages * kStageBytes + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        B2_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    CUtensorMap map_c;
+    B2_TRY(make_map(&map_c, s->dense.p, s->n_rows, s->dim, kGemmN));
+    s->stats.dense_path = 2;
+    s->stats.dense_passes = 0;
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
+    for (int q0 = 0; q0 < batch; q0 += kGemmM) {
+        const int nq = batch - q0 < kGemmM ? batch - q0 : kGemmM;
+        CUtensorMap map_q;
+        B2_TRY(make_map(&map_q, s->ws.q_bits.as<uint16_t>() + (size_t)q0 * s->dim, nq, s->dim, kGemmM));
+        GemmParams p{};
+        p.n_rows = s->n_rows;
+        p.n_tiles = n_tiles;
+        p.dim = s->dim;
+        p.batch = nq;
+        p.masks = s->h_masks.empty() ? nullptr : s->ws.q_masks.as<const uint32_t*>() + q0;
+        p.g_thr = s->ws.thr.as<uint64_t>() + q0;
+        p.out = out_lists + (size_t)q0 * grid * Lc;
+        p.out_q_stride = (int64_t)grid * Lc;
+        p.Lc = Lc;
+        p.dbg_scores = dbg_scores != nullptr ? dbg_scores + (size_t)q0 * s->n_rows : nullptr;
+        dense_gemm_kernel<<<grid, kGemmThreads, smem, s->stream>>>(map_q, map_c, p);
+        B2_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        s->stats.dense_passes++;
+    }
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[1], s->stream)); s->ev_dense = true; }
+    s->stats.dense_bytes = (int64_t)s->stats.dense_passes * s->n_rows * s->dim * 2;
+    return B200RAG_OK;
+}
+
+}  // namespace b200rag

@@ -144,7 +144,9 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_TRY(s->ws.lists_a.ensure((size_t)B * nl_max * Lc * 8, 0, st));
             B2_TRY(s->ws.lists_b.ensure((size_t)B * nl_max * Lc * 8, 0, st));
             int nlists = 0;
-            B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
+            const bool use_gemm = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
+            if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
+            else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
             uint64_t* approx = nullptr;
             B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
             B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
@@ -292,6 +294,30 @@ int b200rag_set_slack(b200rag_shard* sp, int32_t slack) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || slack < 0) { set_error("set_slack: bad argument"); return B200RAG_ERR_INVALID; }
     s->slack = slack;
+    return B200RAG_OK;
+}
+
+int b200rag_set_dense_path(b200rag_shard* sp, int32_t path) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || path < 0 || path > 2) { set_error("set_dense_path: bad argument"); return B200RAG_ERR_INVALID; }
+    s->dense_path = path;
+    return B200RAG_OK;
+}
+
+int b200rag_debug_dense_scores(b200rag_shard* sp, float* out_scores_dev) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || out_scores_dev == nullptr) { set_error("debug_dense_scores: null argument"); return B200RAG_ERR_INVALID; }
+    if (!s->staged || s->q.mode == B200RAG_SPARSE) { set_error("debug_dense_scores: stage a dense/hybrid batch first"); return B200RAG_ERR_STATE; }
+    if (s->n_rows == 0) return B200RAG_OK;
+    B2_TRY(use_device(s));
+    const int B = s->q.batch, Lc = 16;
+    B2_TRY(s->ws.thr.ensure((size_t)(B + 1) * 8, 0, s->stream));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + B;
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, s->stream));
+    B2_TRY(s->ws.lists_a.ensure((size_t)B * dense_gemm_nlists(s) * Lc * 8, 0, s->stream));
+    int nlists = 0;
+    B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, out_scores_dev));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
     return B200RAG_OK;
 }
 

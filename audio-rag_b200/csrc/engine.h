@@ -72,6 +72,7 @@ struct Shard {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int slack = 0;
+    int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
 
     // dense rows
     int64_t n_rows = 0;
@@ -119,6 +120,11 @@ struct Shard {
 // SIMT bulk-copy scan: approximate fp32 scores, per-CTA top-Lc key lists.  Returns number of lists per query.
 int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, int* nlists);
 int dense_scan_nlists(const Shard* s);
+
+// ---- dense_umma.cu --------------------------------------------------------------------------------------
+// tcgen05 + TMA GEMM with the top-k fused in the TMEM epilogue (<= 128 queries per corpus pass). Same output format.
+int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores);
+int dense_gemm_nlists(const Shard* s);
 
 // ---- select.cu -----------------------------------------------------------------------------------------
 // Reduce [batch, n_lists, Lc] key lists to [batch, Lc] (sorted desc) with a tree of smem bitonic merges.

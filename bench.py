@@ -118,7 +118,7 @@ def run_reference(a):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),
             "cpu_baseline": detail,
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- clocks sampler
@@ -362,14 +362,27 @@ def run_b200(a):
             except Exception as e:  # the oracle is a checker, never a dependency of the measured path
                 line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was re-routed."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # NCCL / CUDA libraries print to fd 1 ("NCCL version ..."): keep the contract of exactly one JSON line on stdout
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

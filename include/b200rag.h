@@ -94,6 +94,11 @@ void b200rag_shard_destroy(b200rag_shard* s);
 int b200rag_set_stream(b200rag_shard* s, void* cuda_stream);
 int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximate candidates per leg before the
                                                                 exact re-score (0 = default max(16, L/2))      */
+/* Dense kernel choice: 0 = auto (bulk-copy SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT scan,
+ * 2 = tcgen05 GEMM.  Both produce bit-identical results (candidates are re-scored in the canonical order). */
+int b200rag_set_dense_path(b200rag_shard* s, int32_t path);
+/* Test hook: run the tcgen05 GEMM on the staged batch and write its raw approximate scores [batch, rows] (fp32). */
+int b200rag_debug_dense_scores(b200rag_shard* s, float* out_scores_dev);
 int b200rag_sync(b200rag_shard* s);
 
 /* ---- ingest  (replaces client.upsert, qdrant.py:197-220) ---------------------------------------------- */

@@ -266,3 +266,52 @@ def test_two_shards_fuse_equals_one(gpu):
         assert g["valid"].max() == 1
     for sh in (one, a, b):
         sh.close()
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM path
+@pytest.mark.parametrize("dim,n,B", [(1024, 1000, 5), (256, 777, 3), (768, 5000, 130), (1024, 40_000, 64)])
+def test_gemm_raw_scores_match_fp32_matmul(gpu, dim, n, B):
+    """The tensor-core path as a GEMM: raw fp32-accumulated scores of every (query, row) pair against numpy on the
+    same bf16 bits (fp32 accumulate tolerance: 1e-5 absolute on unit vectors, the north star's fp32 bound)."""
+    import torch
+    from b200rag import Shard, normalize_bf16, synth
+    c = Corpus(n, dim=dim, sparse=False)
+    sh = Shard(dim=dim, vocab=1000, device=gpu)
+    sh.add(c.bits)
+    qf, _, _, _ = c.queries(B)
+    qb = normalize_bf16(qf)
+    q, keep = sh.make_query("dense", 10, qb)
+    sh.stage(q, keep)
+    out = torch.full((B, n), float("nan"), dtype=torch.float32, device=torch.device("cuda", gpu))
+    sh.debug_dense_scores(out)
+    got = out.cpu().numpy()
+    exp = synth.bf16_bits_to_f32(qb).astype(np.float64) @ synth.bf16_bits_to_f32(c.bits).astype(np.float64).T
+    assert not np.isnan(got).any()
+    err = np.abs(got - exp).max()
+    assert err < 1e-5, f"max abs err {err}"
+    sh.close()
+
+
+@pytest.mark.parametrize("B,top_k", [(1, 10), (3, 10), (64, 10), (130, 5), (7, 100)])
+def test_dense_parity_gemm_path(gpu, B, top_k):
+    c = Corpus(30_011, dim=1024, sparse=False)
+    sh = _shard_from(c, gpu)
+    sh.set_dense_path(2)
+    _run_and_check(sh, c, "dense", B, top_k, batch=B)
+    assert sh.stats()["dense_path"] == 2
+    sh.close()
+
+
+def test_hybrid_masks_gemm_path(gpu):
+    from b200rag import synth
+    c = Corpus(12_345, dim=256, vocab=30_011)
+    sh = _shard_from(c, gpu, docs_per_block=4096)
+    sh.set_dense_path(2)
+    coll = synth.row_collections(c.seed, 0, c.n, 5)
+    masks = {m: coll == m for m in range(5)}
+    for m in range(5):
+        sh.mask_set(m, synth.pack_mask(masks[m]), c.n)
+    mask_ids = [0, 3, -1, 4, 1, 2, 2, 0]
+    _run_and_check(sh, c, "hybrid", 8, 10, masks=masks, mask_ids=mask_ids, batch=8)
+    _run_and_check(sh, c, "dense", 8, 10, masks=masks, mask_ids=mask_ids, batch=4)
+    sh.close()

@@ -1,0 +1,58 @@
+"""torchrun check of the sharded GPU path against the oracle (run under gpurun --gpus N):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dist_check.py
+Every rank holds a row range on its own GPU; fused results must be identical on all ranks and bit-equal to the
+single-index oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "audio-rag_b200"), os.path.join(ROOT, "tests")]
+from b200rag import Shard, normalize_bf16  # noqa: E402
+from b200rag.dist import ShardedSearcher, shard_bounds  # noqa: E402
+from helpers import Corpus, oracle_search  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    n, dim = 40_000, 1024
+    c = Corpus(n, dim=dim, vocab=60_013)
+    lo, hi = shard_bounds(n, world, rank, align=16)
+    sh = Shard(dim=dim, vocab=c.vocab, device=local, row_base=lo, docs_per_block=2048)
+    sh.set_stream(torch.cuda.current_stream().cuda_stream)
+    sh.add(c.bits[lo:hi], c.indptr[lo:hi + 1] - c.indptr[lo], c.terms[c.indptr[lo]:c.indptr[hi]],
+           c.w[c.indptr[lo]:c.indptr[hi]])
+    ss = ShardedSearcher(sh, dev)
+    qf, ip, tt, ww = c.queries(6)
+    qb = normalize_bf16(qf)
+    bad = 0
+    for mode, k, B in (("dense", 10, 1), ("sparse", 10, 3), ("hybrid", 10, 1), ("hybrid", 5, 6), ("hybrid", 100, 2)):
+        for s in range(0, 6, B):
+            e = s + B
+            ids, sc, cnt = ss.search(mode, k, qb[s:e], ip[s:e + 1] - ip[s], tt[ip[s]:ip[e]], ww[ip[s]:ip[e]])
+            for b in range(s, e):
+                ei, es = oracle_search(c, mode, qb[b], tt[ip[b]:ip[b + 1]], ww[ip[b]:ip[b + 1]], None, k)
+                ok = cnt[b - s] == len(ei) and np.array_equal(ids[b - s, :len(ei)], ei) and \
+                    np.array_equal(sc[b - s, :len(ei)], es)
+                bad += 0 if ok else 1
+            t = torch.from_numpy(ids.copy()).to(dev)
+            ref = t.clone()
+            dist.broadcast(ref, src=0)
+            bad += 0 if torch.equal(t, ref) else 1
+    tot = torch.tensor([bad], device=dev)
+    dist.all_reduce(tot)
+    if rank == 0:
+        print(f"dist_check world={world}: mismatches={int(tot.item())}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(tot.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
