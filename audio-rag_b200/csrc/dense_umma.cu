@@ -8,9 +8,11 @@
 // both operands bf16 K-major in shared memory with the 128-byte swizzle, K = dim stepped 64 elements per
 // pipeline stage (16 KB of queries + 32 KB of corpus rows per stage, 4 stages), 4 x tcgen05.mma (K = 16) per stage.
 // Queries are the M dimension on purpose: TMEM lane i then holds query i, so ONE epilogue thread owns ONE query and
-// can keep that query's running top-Lc threshold in a register and its sorted candidate list privately (no atomics,
-// no CTA-wide compaction).  The list is a sorted array in global memory (L1/L2 resident, touched only on the rare
-// insertion); thresholds are shared grid-wide through a monotone atomicMax like in the SIMT scan.
+// keeps that query's running top-Lc threshold in a register: the common case per score is one FSETP.  Survivors are
+// inserted into the query's sorted list in shared memory by the whole warp (ballot over the 32 queries of the warp,
+// then a cooperative shift), so an insert costs O(Lc/32) steps, not O(Lc); thresholds are shared grid-wide through a
+// monotone atomicMax like in the SIMT scan.  DRAM sees contiguous reads: each 256-row tile (512 KB) is prefetched into
+// L2 as one bulk region two tiles ahead, the 128-byte-wide tensor loads then hit L2.
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over 256-row corpus tiles):
 //   warp 0  TMA producer   (one lane): cp.async.bulk.tensor.2d of the query k-block and the corpus k-block
@@ -39,6 +41,7 @@ constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
 constexpr uint32_t kTmemCols = 512;
 
 struct GemmParams {
+    const void* corpus;            // for the contiguous L2 prefetch
     int64_t n_rows;
     int64_t n_tiles;
     int dim;
@@ -48,6 +51,7 @@ struct GemmParams {
     uint64_t* out;                 // [batch][grid][Lc]
     int64_t out_q_stride;          // grid * Lc
     int Lc;
+    int stages;                    // pipeline depth actually used (2..kGemmStages), set by the launcher
     float* dbg_scores;             // optional [batch][n_rows] raw approximate scores (tests)
 };
 
@@ -97,6 +101,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// contiguous L2 prefetch (bulk, 1-D): lets DRAM stream whole 2 KB rows while the tensor loads below pick 128-byte
+// k-slices of 256 different rows per stage
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// Candidate lists in shared memory, one per query: an UNSORTED set of the Lc best keys seen so far plus, in the
+// owning lane's registers, the fill count and the position/value of the current minimum (= the running threshold).
+// An insert overwrites the minimum and rescans for the new one: Lp/2 independent 128-bit loads, no shifting, so
+// the cost does not depend on where the key ranks and up to 32 lanes insert in the same round.  Lists are sorted
+// once, at the end of the kernel.  Lp = Lc rounded up to even (a pad slot holds ~0 and is never the minimum).
+__device__ __forceinline__ void lane_replace(uint64_t* lst, int Lc, int Lp, uint64_t key, int& cnt, int& minpos,
+                                             uint64_t& lmin) {
+    if (cnt < Lc) {
+        lst[cnt++] = key;
+        if (cnt < Lc) return;
+    } else {
+        lst[minpos] = key;
+    }
+    uint64_t m = ~0ull;
+    int mp = 0;
+    const ulonglong2* l2 = reinterpret_cast<const ulonglong2*>(lst);
+#pragma unroll 4
+    for (int i = 0; i < Lp / 2; ++i) {
+        const ulonglong2 kk = l2[i];
+        if (kk.x < m) { m = kk.x; mp = 2 * i; }
+        if (kk.y < m) { m = kk.y; mp = 2 * i + 1; }
+    }
+    minpos = mp;
+    lmin = m;
+}
+
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -105,17 +141,26 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
                             ((uint32_t)(kGemmM >> 4) << 24);
 
+// LREG > 0: each epilogue lane keeps its query's candidate list SORTED IN REGISTERS (LREG keys; Lc <= LREG; the
+//           threshold is the LREG-th best, slightly weaker than the Lc-th, which only admits a few more inserts).
+//           A sorted insert is LREG independent compare/selects: no memory, no dependent chain.
+// LREG == 0: lists live in shared memory (unsorted, replace-min) for large top-k.
+template <int LREG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                   const GemmParams p) {
     extern __shared__ uint8_t gsm_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles
-    uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + (size_t)kGemmStages * kStageBytes);
+    // (offset arithmetic on the shared window keeps the pointer in the shared address space: LDS/STS, not generic)
+    uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
+    const int S = p.stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);
     uint64_t* empty = full + kGemmStages;
     uint64_t* tfull = empty + kGemmStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 2);   // (16 u64 barrier slots precede: 16-byte aligned)
+    float* stage_s = reinterpret_cast<float*>(tmem_base_s + 4);          // [4 epilogue warps][32 lanes][33] score staging
+    uint64_t* lists_s = reinterpret_cast<uint64_t*>(stage_s + 4 * 32 * 33);       // [ceil32(batch)][Lp], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.dim / kGemmKB;
@@ -125,7 +170,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_q);
         prefetch_tmap(&map_c);
-        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         fence_mbar_init();
     }
@@ -147,7 +192,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     mbar_arrive_expect_tx(&full[st], kStageBytes);
                     tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
                     tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * kGemmN));
-                    if (++st == kGemmStages) { st = 0; ph ^= 1u; }
+                    if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
         }
@@ -174,7 +219,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                   (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty[st]);             // frees the smem stage when these MMAs retire
                     if (kb == nkb - 1) umma_commit(&tfull[buf]);
-                    if (++st == kGemmStages) { st = 0; ph ^= 1u; }
+                    if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
         }
@@ -183,12 +228,22 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int quad = warp - 4;                       // == warp % 4: the TMEM lane quadrant this warp may read
         const int qi = quad * 32 + lane;                 // my query
         const bool active = qi < p.batch;
-        uint64_t* list = p.out + (size_t)(active ? qi : 0) * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+        const bool warp_active = quad * 32 < p.batch;
+        const int Lp = (p.Lc + 1) & ~1;
+        uint64_t* wlists = lists_s + (size_t)(quad * 32) * Lp;     // this warp's 32 lists (LREG == 0 only)
         const uint32_t* mask = (active && p.masks != nullptr) ? p.masks[qi] : nullptr;
-        if (active)
-            for (int i = 0; i < p.Lc; ++i) list[i] = 0;
-        int cnt = 0;
-        uint64_t thr = 0;
+        uint64_t L[LREG > 0 ? LREG : 1];
+#pragma unroll
+        for (int i = 0; i < (LREG > 0 ? LREG : 1); ++i) L[i] = 0;
+        if (LREG == 0 && warp_active) {
+            for (int i = lane; i < 32 * Lp; i += 32) wlists[i] = 0;
+            __syncwarp();
+            if (Lp != p.Lc) wlists[(size_t)lane * Lp + p.Lc] = ~0ull;
+        }
+        __syncwarp();
+        uint64_t thr = 0;          // acceptance threshold: max(my list's minimum once full, grid-wide threshold)
+        uint64_t lmin = 0;         // my list's minimum (0 until the list is full)
+        int cnt = 0, minpos = 0;
         float thr_s = -INFINITY;
         int it = 0;
         for (int64_t t = t0; t < t1; ++t, ++it) {
@@ -204,41 +259,83 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
-                if (!active) continue;
+                if (!warp_active) continue;
                 const int64_t row0 = t * kGemmN + c * 32;
+                if (p.dbg_scores != nullptr && active) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]) + 0.0f;
-                    const int64_t row = row0 + j;
-                    if (p.dbg_scores != nullptr && row < p.n_rows) p.dbg_scores[(size_t)qi * p.n_rows + row] = s;
-                    if (s >= thr_s && row < p.n_rows) {
-                        const uint64_t key = make_key(s, (uint32_t)row);
-                        if (key > thr) {
-                            bool ok = true;
-                            if (mask != nullptr) ok = (mask[row >> 5] >> (row & 31)) & 1u;
-                            if (ok) {
-                                // sorted insert into my private list (descending)
-                                int i = cnt < p.Lc ? cnt : p.Lc - 1;
-                                while (i > 0 && list[i - 1] < key) { list[i] = list[i - 1]; --i; }
-                                list[i] = key;
-                                if (cnt < p.Lc) ++cnt;
-                                if (cnt == p.Lc) {
-                                    const uint64_t nt = list[p.Lc - 1];
-                                    if (nt > thr) {
-                                        thr = nt;
-                                        thr_s = key_score(nt);
-                                        atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[qi]),
-                                                  (unsigned long long)nt);
-                                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (row0 + j < p.n_rows)
+                            p.dbg_scores[(size_t)qi * p.n_rows + row0 + j] = __uint_as_float(v[j]) + 0.0f;
+                }
+                // phase A: one compare per score against my query's threshold (registers only)
+                uint32_t cm = 0;
+                if (active) {
+                    const int nvalid = p.n_rows - row0 < 32 ? (int)(p.n_rows - row0) : 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        cm |= ((__uint_as_float(v[j]) + 0.0f >= thr_s) && j < nvalid) ? (1u << j) : 0u;
+                }
+                if (!__any_sync(0xffffffffu, cm != 0)) continue;
+                // phase B (rare after warm-up): stage the chunk's scores, then insert survivors
+                float* stg = stage_s + (size_t)quad * 32 * 33;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]) + 0.0f;
+                __syncwarp();
+                // every lane with survivors inserts one of its own per round (up to 32 inserts per round)
+                while (__any_sync(0xffffffffu, cm != 0)) {
+                    if (cm != 0) {
+                        const int j = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const int64_t row = row0 + j;
+                        const uint64_t key = make_key(stg[lane * 33 + j], (uint32_t)row);
+                        bool ok = key > thr;
+                        if (ok && mask != nullptr) ok = (mask[row >> 5] >> (row & 31)) & 1u;
+                        if (ok) {
+                            if constexpr (LREG > 0) {
+                                // sorted insert (descending), every element decided from OLD neighbours: no chain
+#pragma unroll
+                                for (int i = LREG - 1; i >= 1; --i) {
+                                    const bool gi = key > L[i], gm = key > L[i - 1];
+                                    L[i] = gi ? (gm ? L[i - 1] : key) : L[i];
                                 }
+                                L[0] = key > L[0] ? key : L[0];
+                                lmin = L[LREG - 1];
+                            } else {
+                                lane_replace(wlists + (size_t)lane * Lp, p.Lc, Lp, key, cnt, minpos, lmin);
+                            }
+                            if (lmin > thr) {
+                                thr = lmin;
+                                thr_s = key_score(lmin);
+                                atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[qi]), (unsigned long long)lmin);
                             }
                         }
+                        // survivors flagged against the chunk-start threshold that the new threshold rules out
+                        while (cm != 0 && stg[lane * 33 + (__ffs(cm) - 1)] < thr_s) cm &= cm - 1;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        __syncwarp();
+        if constexpr (LREG > 0) {
+            // my list is already sorted: first Lc keys -> global [q][cta][Lc]
+            if (active) {
+                uint64_t* o = p.out + (size_t)qi * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+#pragma unroll
+                for (int i = 0; i < LREG; ++i)
+                    if (i < p.Lc) o[i] = L[i];
+            }
+        } else if (warp_active) {
+            // unsorted lists -> global [q][cta][Lc]; the merge tree sorts (it never assumes order)
+            for (int ql = 0; ql < 32; ++ql) {
+                const int q = quad * 32 + ql;
+                if (q >= p.batch) break;
+                const uint64_t* src_l = wlists + (size_t)ql * Lp;
+                uint64_t* o = p.out + (size_t)q * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+                for (int i = lane; i < p.Lc; i += 32) o[i] = src_l[i];
+            }
         }
     }
 
@@ -284,27 +381,52 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, i
 
 int dense_gemm_nlists(const Shard* s) { return s->sm_count; }
 
+template <int LREG>
+static int launch_gemm_t(Shard* s, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmParams& p, int grid,
+                         size_t smem) {
+    auto kern = dense_gemm_kernel<LREG>;
+    static bool attr = false;
+    if (!attr) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    kern<<<grid, kGemmThreads, smem, s->stream>>>(map_q, map_c, p);
+    B2_CUDA(cudaGetLastError());
+    return B200RAG_OK;
+}
+
 int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores) {
     const int64_t n_tiles = (s->n_rows + kGemmN - 1) / kGemmN;
     int grid = s->sm_count;
     if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
     *nlists = grid;
-    const size_t smem = (size_t)kGemmStages * kStageBytes + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
-        B2_CUDA(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+    const int lreg = Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0);
+    // shared memory: S pipeline stages (48 KB each) + score staging (+ one list of Lc keys per query when the lists
+    // do not fit in registers)
+    const size_t max_smem = 227 * 1024, fixed = 1024 + 512 + 4 * 32 * 33 * 4;
+    const int Lp = (Lc + 1) & ~1;
+    const size_t per_q = lreg ? 0 : (size_t)Lp * 8;
+    int qpp = kGemmM;                                   // queries per pass
+    while (qpp > 32 && fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) qpp -= 32;
+    if (fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) {
+        set_error("dense_gemm: top-k too large for shared memory");
+        return B200RAG_ERR_INVALID;
     }
     CUtensorMap map_c;
     B2_TRY(make_map(&map_c, s->dense.p, s->n_rows, s->dim, kGemmN));
     s->stats.dense_path = 2;
     s->stats.dense_passes = 0;
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
-    for (int q0 = 0; q0 < batch; q0 += kGemmM) {
-        const int nq = batch - q0 < kGemmM ? batch - q0 : kGemmM;
+    for (int q0 = 0; q0 < batch; q0 += qpp) {
+        const int nq = batch - q0 < qpp ? batch - q0 : qpp;
+        const size_t list_bytes = (size_t)((nq + 31) / 32 * 32) * per_q;
+        int stages = (int)((max_smem - fixed - list_bytes) / kStageBytes);
+        if (stages > kGemmStages) stages = kGemmStages;
+        const size_t smem = fixed + (size_t)stages * kStageBytes + list_bytes;
         CUtensorMap map_q;
         B2_TRY(make_map(&map_q, s->ws.q_bits.as<uint16_t>() + (size_t)q0 * s->dim, nq, s->dim, kGemmM));
         GemmParams p{};
+        p.corpus = s->dense.p;
         p.n_rows = s->n_rows;
         p.n_tiles = n_tiles;
         p.dim = s->dim;
@@ -314,9 +436,11 @@ int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.out = out_lists + (size_t)q0 * grid * Lc;
         p.out_q_stride = (int64_t)grid * Lc;
         p.Lc = Lc;
+        p.stages = stages;
         p.dbg_scores = dbg_scores != nullptr ? dbg_scores + (size_t)q0 * s->n_rows : nullptr;
-        dense_gemm_kernel<<<grid, kGemmThreads, smem, s->stream>>>(map_q, map_c, p);
-        B2_CUDA(cudaGetLastError());
+        if (lreg == 32) B2_TRY(launch_gemm_t<32>(s, map_q, map_c, p, grid, smem));
+        else if (lreg == 64) B2_TRY(launch_gemm_t<64>(s, map_q, map_c, p, grid, smem));
+        else B2_TRY(launch_gemm_t<0>(s, map_q, map_c, p, grid, smem));
         s->stats.kernel_launches++;
         s->stats.dense_passes++;
     }

@@ -292,7 +292,7 @@ def test_gemm_raw_scores_match_fp32_matmul(gpu, dim, n, B):
     sh.close()
 
 
-@pytest.mark.parametrize("B,top_k", [(1, 10), (3, 10), (64, 10), (130, 5), (7, 100)])
+@pytest.mark.parametrize("B,top_k", [(1, 10), (3, 10), (64, 10), (130, 5), (7, 100), (40, 20)])
 def test_dense_parity_gemm_path(gpu, B, top_k):
     c = Corpus(30_011, dim=1024, sparse=False)
     sh = _shard_from(c, gpu)

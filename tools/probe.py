@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--R", type=int, default=0)
+    ap.add_argument("--dense-path", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -63,6 +64,8 @@ def main():
     sh = build_shard(a.rows, a.dim, sparse, dev, a.R)
     torch.cuda.synchronize()
     print(f"shard built in {time.time() - t:.1f}s rows={sh.count}", flush=True)
+    sh.set_dense_path(a.dense_path)
+    sh.set_profiling(True)
     for mode in modes:
         for B in [int(x) for x in a.batches.split(",")]:
             qf = synth.dense_queries_f32(2000, 0, B, a.rows, a.dim, corpus_seed=1234)
@@ -92,7 +95,8 @@ def main():
             p50 = ms[len(ms) // 2]
             gb = st["dense_bytes"] / 1e9
             print(f"mode={mode} B={B} p50={p50:.3f}ms min={ms[0]:.3f}ms launches={st['kernel_launches']} "
-                  f"dense_GB={gb:.3f} dense_GB/s(p50)={gb / (p50 / 1e3):.0f} amb={int(amb.item())} "
+                  f"dense_GB={gb:.3f} dense_GB/s(p50)={gb / (p50 / 1e3):.0f} scan_ms={st['dense_scan_ms']:.3f} "
+                  f"scan_GB/s={gb / max(st['dense_scan_ms'], 1e-9) * 1e3:.0f} TF={2.0 * B * a.rows * a.dim / max(st['dense_scan_ms'], 1e-9) / 1e9:.1f} sparse_ms={st['sparse_scan_ms']:.3f} amb={int(amb.item())} "
                   f"ids0={oi[0, :3].tolist()} cnt={oc[0].item()}", flush=True)
             # wall-clock through the host-buffer call
             t0 = time.perf_counter()
