@@ -257,6 +257,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         }
         int stages = (int)((max_smem - buf_bytes - 256) / stage_bytes);
         if (stages > 8) stages = 8;
+        if (s->dense_stage_cap > 0 && stages > s->dense_stage_cap) stages = s->dense_stage_cap;
         while ((size_t)stages * stage_bytes < merge_bytes) ++stages;
         if (stages < 2) { set_error("dense_scan: top-k too large for shared memory"); return B200RAG_ERR_INVALID; }
         const size_t smem = (size_t)stages * stage_bytes + (size_t)stages * 16 + buf_bytes;

@@ -1,5 +1,6 @@
 // C-ABI entry points of libb200rag.so (include/b200rag.h) and the host-side orchestration of one shard.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -134,9 +135,19 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     const bool want_sparse = q.mode != B200RAG_DENSE;
     if (want_sparse && s->built_rows != s->n_rows) B2_TRY(build_inverted(s));
 
-    int leg = 0;
+    // Hybrid: the sparse leg (scan + merges + exact re-score) runs on the side stream while the dense scan streams the
+    // corpus.  The dense scan is issued FIRST so its persistent CTAs (1 per SM, ring capped at 5 stages = 168 KB) are
+    // resident, and one 46 KB sparse CTA per SM co-resides with them.
+    const bool overlap = want_dense && want_sparse && s->overlap_legs && s->side_stream != nullptr && s->n_rows > 0 &&
+                         (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows);
+    b200rag_cand* out_dense = cands;
+    b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
+    if (overlap) {
+        B2_CUDA(cudaEventRecord(s->ev_fork, st));
+        B2_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+    }
     if (want_dense) {
-        b200rag_cand* out = cands + (size_t)leg * B * L;
+        b200rag_cand* out = out_dense;
         if (s->n_rows == 0) {
             B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), st));
         } else {
@@ -145,31 +156,40 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_TRY(s->ws.lists_b.ensure((size_t)B * nl_max * Lc * 8, 0, st));
             int nlists = 0;
             const bool use_gemm = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
+            s->dense_stage_cap = overlap ? 5 : s->dense_stage_cap_env;
             if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
             else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
+            s->dense_stage_cap = 0;
             uint64_t* approx = nullptr;
             B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
             B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
             B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f,
                                        q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, out, ambiguous));
         }
-        ++leg;
     }
     if (want_sparse) {
-        b200rag_cand* out = cands + (size_t)leg * B * L;
+        b200rag_cand* out = out_sparse;
+        cudaStream_t sst = overlap ? s->side_stream : st;
         if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) {
-            B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), st));
+            B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), sst));
         } else {
             const size_t need = (size_t)B * s->n_blocks * Lc * 8;
-            B2_TRY(s->ws.lists_a.ensure(need, 0, st));
-            B2_TRY(s->ws.lists_b.ensure(need, 0, st));
-            B2_TRY(launch_sparse_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>()));
+            B2_TRY(s->ws.lists_c.ensure(need, 0, st));
+            B2_TRY(s->ws.lists_d.ensure(need, 0, st));
+            B2_TRY(s->ws.exact2.ensure((size_t)B * Lc * 8, 0, st));
+            s->stream = sst;                                   // the launchers below enqueue on s->stream
+            int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>());
             uint64_t* approx = nullptr;
-            B2_TRY(launch_merge_tree(s, B, (int)s->n_blocks, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
-            B2_TRY(launch_rescore_sparse(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
-            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 1e-12f, 4e-5f, 0, 0.f, out, ambiguous));
+            if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, (int)s->n_blocks, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
+            if (rc == B200RAG_OK) rc = launch_rescore_sparse(s, B, Lc, approx, s->ws.exact2.as<uint64_t>());
+            if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 4e-5f, 0, 0.f, out, ambiguous);
+            s->stream = st;
+            if (rc != B200RAG_OK) return rc;
         }
-        ++leg;
+    }
+    if (overlap) {
+        B2_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
+        B2_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     }
     (void)nlegs;
     return B200RAG_OK;
@@ -249,6 +269,15 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaStreamCreate"); }
     s->stream = s->own_stream;
+    if (cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        s->side_stream = nullptr;   // no overlap, still correct
+    }
+    if (const char* e = getenv("B200RAG_OVERLAP")) s->overlap_legs = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_OVERLAP_MAX_ROWS")) s->overlap_max_rows = atoll(e);
+    if (const char* e = getenv("B200RAG_DENSE_STAGES")) s->dense_stage_cap_env = atoi(e);
     int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);
     if (rc == B200RAG_OK) {
         e = cudaMemsetAsync(s->fwd_ptr.p, 0, 8, s->stream);
@@ -274,9 +303,13 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     for (auto& kv : s->masks) kv.second.release();
     s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
     s->ws.exact.release(); s->ws.cands.release(); s->ws.out.release();
+    s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (int i = 0; i < 4; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }

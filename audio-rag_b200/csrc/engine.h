@@ -38,7 +38,7 @@ struct DevBuf {
 constexpr int kMaxBatchMasks = 4096;
 constexpr int kScanConsumerWarps = 8;
 constexpr int kScanTileRows = 16;
-constexpr int kSparseThreads = 512;
+constexpr int kSparseThreads = 256;
 constexpr int kMaxQueryTermsChunk = 256;
 constexpr int kMergeMaxKeys = 8192;    // smem bound of one merge group
 constexpr int kMergeGroupKeys = 1024;  // preferred group size (keeps the bitonic network short)
@@ -61,6 +61,9 @@ struct Workspace {
     DevBuf lists_a;       // candidate key lists (ping)
     DevBuf lists_b;       // candidate key lists (pong)
     DevBuf exact;         // [B, Lc] u64 exact keys
+    DevBuf lists_c;       // second set for the sparse leg, which runs concurrently on the side stream
+    DevBuf lists_d;
+    DevBuf exact2;
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
 };
@@ -71,6 +74,12 @@ struct Shard {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // sparse leg of a hybrid search overlaps the dense scan here
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_legs = true;
+    int64_t overlap_max_rows = 0;         // overlap only shards up to this many rows (0 = always); tuning knobs via env
+    int dense_stage_cap_env = 0;
+    int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
 

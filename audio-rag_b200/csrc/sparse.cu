@@ -27,7 +27,7 @@
 
 namespace b200rag {
 
-constexpr int kSelCap = 2048;
+constexpr int kSelCap = 1024;
 
 struct SparseScanParams {
     const uint32_t* dir;
@@ -148,28 +148,49 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
     }
     if (tid == 0 && p.post_count != nullptr) atomicAdd(p.post_count, npost_s);
 
-    // ---- selection: keys of my EPT strided documents
+    // ---- selection.  Keys are recomputed from the accumulators on each pass (keeps registers low -> more CTAs/SM).
     const uint32_t* m = p.masks != nullptr ? p.masks[q] : nullptr;
-    uint64_t mykeys[EPT];
-    uint64_t tmax = 0;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
+    auto key_of = [&](int i) -> uint64_t {
         const int idx = i * NT + tid;
         const float v = acc[idx];
         const uint32_t doc = (uint32_t)b * (uint32_t)R + (uint32_t)idx;
         bool ok = __float_as_uint(v) != 0x80000000u;
         if (ok && m != nullptr) ok = (m[doc >> 5] >> (doc & 31)) & 1u;
-        const uint64_t k = ok ? make_key(v, doc) : 0ull;
-        mykeys[i] = k;
+        return ok ? make_key(v, doc) : 0ull;
+    };
+    uint64_t tmax = 0;
+#pragma unroll 8
+    for (int i = 0; i < EPT; ++i) {
+        const uint64_t k = key_of(i);
         tmax = k > tmax ? k : tmax;
     }
-    sel[tid] = tmax;
-    cta_bitonic_desc(sel, NT, tid, NT, 0);
-    const uint64_t tau = p.Lc <= NT ? sel[p.Lc - 1] : 0ull;
-    __syncthreads();
+    // threshold: every warp sorts its 32 thread maxima in registers and publishes its k-th largest, k = ceil(Lc / #warps);
+    // the minimum over the warps has >= Lc distinct documents at or above it, so it is a valid lower bound for the
+    // block's Lc-th best key (no block-wide sort, one barrier).
+    constexpr int NW = NT / 32;
+    __shared__ uint64_t wk_s[NW];
+    {
+        const int lane = tid & 31;
+        uint64_t v = tmax;
 #pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool keep_max = (((lane & j) == 0) == ((lane & k) == 0));
+                v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+            }
+        const int kk = (p.Lc + NW - 1) / NW;
+        const uint64_t kth = kk <= 32 ? __shfl_sync(0xffffffffu, v, kk - 1) : 0ull;
+        if (lane == 0) wk_s[tid >> 5] = kth;
+    }
+    __syncthreads();
+    uint64_t tau = wk_s[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) tau = wk_s[w] < tau ? wk_s[w] : tau;
+#pragma unroll 8
     for (int i = 0; i < EPT; ++i) {
-        const uint64_t k = mykeys[i];
+        const uint64_t k = key_of(i);
         if (k != 0 && k >= tau) {
             const int pos = atomicAdd(&cnt_s, 1);
             if (pos < kSelCap) sel[pos] = k;
@@ -178,15 +199,14 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
     __syncthreads();
     int M = cnt_s;
     if (M > kSelCap) {
-        // Rare: more than kSelCap documents tie above the threshold estimate.  Find the exact Lc-th largest
-        // key by bisection on the key bits (keys are unique), then collect exactly the keys >= it.
+        // Rare: more than kSelCap documents at or above the threshold estimate (e.g. massive ties).  Find the exact
+        // Lc-th largest key by bisection on the key bits (keys are unique), then collect exactly the keys >= it.
         __shared__ int c_s;
         uint64_t K = 0;
         for (int bit = 63; bit >= 0; --bit) {
             const uint64_t cand = K | (1ull << bit);
             int c = 0;
-#pragma unroll
-            for (int i = 0; i < EPT; ++i) c += mykeys[i] >= cand ? 1 : 0;
+            for (int i = 0; i < EPT; ++i) c += key_of(i) >= cand ? 1 : 0;
             if (tid == 0) c_s = 0;
             __syncthreads();
             c = __reduce_add_sync(0xffffffffu, c);
@@ -197,12 +217,13 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
         }
         if (tid == 0) cnt_s = 0;
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; ++i)
-            if (mykeys[i] >= K && mykeys[i] != 0) {
+        for (int i = 0; i < EPT; ++i) {
+            const uint64_t k = key_of(i);
+            if (k >= K && k != 0) {
                 const int pos = atomicAdd(&cnt_s, 1);
-                if (pos < kSelCap) sel[pos] = mykeys[i];
+                if (pos < kSelCap) sel[pos] = k;
             }
+        }
         __syncthreads();
         M = cnt_s;
     }
@@ -218,6 +239,7 @@ static int launch_scan_t(Shard* s, const SparseScanParams& p, int batch) {
     const size_t smem = (size_t)EPT * kSparseThreads * 4 + (size_t)kSelCap * 8 + (size_t)kMaxQueryTermsChunk * 24;
     auto kern = sparse_scan_kernel<EPT>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     dim3 grid((unsigned)s->n_blocks, (unsigned)batch);
     kern<<<grid, kSparseThreads, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());
@@ -246,12 +268,12 @@ int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists) {
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[2], s->stream)); }
     int rc;
     switch (s->R / kSparseThreads) {
-        case 2: rc = launch_scan_t<2>(s, p, batch); break;
         case 4: rc = launch_scan_t<4>(s, p, batch); break;
         case 8: rc = launch_scan_t<8>(s, p, batch); break;
         case 16: rc = launch_scan_t<16>(s, p, batch); break;
         case 32: rc = launch_scan_t<32>(s, p, batch); break;
         case 64: rc = launch_scan_t<64>(s, p, batch); break;
+        case 128: rc = launch_scan_t<128>(s, p, batch); break;
         default: set_error("sparse_scan: unsupported docs_per_block"); return B200RAG_ERR_INVALID;
     }
     if (rc == B200RAG_OK && s->profile) { B2_CUDA(cudaEventRecord(s->ev[3], s->stream)); s->ev_sparse = true; }
