@@ -252,6 +252,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const uint64_t g = ld_volatile_u64(&p.g_thr[qi]);
                 if (g > thr) { thr = g; thr_s = key_score(g); }
             }
+            // eligibility of the tile's 256 rows for my query = 8 consecutive words: pull their line towards L1 now,
+            // read one word per chunk below
+            if (mask != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + t * (kGemmN / 32)));
             mbar_wait(&tfull[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kGemmN);
@@ -274,6 +277,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         cm |= ((__uint_as_float(v[j]) + 0.0f >= thr_s) && j < nvalid) ? (1u << j) : 0u;
+                    if (mask != nullptr) cm &= __ldg(mask + t * (kGemmN / 32) + c);
                 }
                 if (!__any_sync(0xffffffffu, cm != 0)) continue;
                 // phase B (rare after warm-up): stage the chunk's scores, then insert survivors
@@ -288,8 +292,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         cm &= cm - 1;
                         const int64_t row = row0 + j;
                         const uint64_t key = make_key(stg[lane * 33 + j], (uint32_t)row);
-                        bool ok = key > thr;
-                        if (ok && mask != nullptr) ok = (mask[row >> 5] >> (row & 31)) & 1u;
+                        const bool ok = key > thr;               // (eligibility was applied to cm already)
                         if (ok) {
                             if constexpr (LREG > 0) {
                                 // sorted insert (descending), every element decided from OLD neighbours: no chain

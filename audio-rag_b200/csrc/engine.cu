@@ -138,8 +138,11 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // Hybrid: the sparse leg (scan + merges + exact re-score) runs on the side stream while the dense scan streams the
     // corpus.  The dense scan is issued FIRST so its persistent CTAs (1 per SM, ring capped at 5 stages = 168 KB) are
     // resident, and one 46 KB sparse CTA per SM co-resides with them.
+    // (only with the SIMT scan, i.e. 1-2 queries: the tcgen05 path fills shared memory, nothing can co-reside with it.
+    // Measured on B200: overlapped beats back-to-back at 1.25M, 10M and 12.5M rows, top-10 and top-100.)
+    const bool use_gemm_path = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
     const bool overlap = want_dense && want_sparse && s->overlap_legs && s->side_stream != nullptr && s->n_rows > 0 &&
-                         (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows);
+                         (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows) && !use_gemm_path;
     b200rag_cand* out_dense = cands;
     b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
     if (overlap) {
@@ -275,7 +278,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
         cudaGetLastError();
         s->side_stream = nullptr;   // no overlap, still correct
     }
-    if (const char* e = getenv("B200RAG_OVERLAP")) s->overlap_legs = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_OVERLAP")) { s->overlap_legs = atoi(e) != 0; s->overlap_force = atoi(e) == 2; }
     if (const char* e = getenv("B200RAG_OVERLAP_MAX_ROWS")) s->overlap_max_rows = atoll(e);
     if (const char* e = getenv("B200RAG_DENSE_STAGES")) s->dense_stage_cap_env = atoi(e);
     int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);

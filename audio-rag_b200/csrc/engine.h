@@ -77,6 +77,7 @@ struct Shard {
     cudaStream_t side_stream = nullptr;   // sparse leg of a hybrid search overlaps the dense scan here
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_legs = true;
+    bool overlap_force = false;
     int64_t overlap_max_rows = 0;         // overlap only shards up to this many rows (0 = always); tuning knobs via env
     int dense_stage_cap_env = 0;
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside

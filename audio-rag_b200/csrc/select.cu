@@ -41,7 +41,7 @@ int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uin
     uint64_t* cur = a;
     uint64_t* nxt = b;
     while (n_lists > 1) {
-        int lpg = kMergeGroupKeys / Lc;
+        int lpg = kMergeGroupKeys / Lc;           // ~1024-key groups: more, cheaper levels beat fewer, bigger sorts
         if (lpg < 2) lpg = 2;
         if (lpg > n_lists) lpg = n_lists;
         const int n_groups = (n_lists + lpg - 1) / lpg;

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
     uint32_t* seg_s_raw = reinterpret_cast<uint32_t*>(qw + kMaxQueryTermsChunk);
     uint32_t* seg_e_raw = seg_s_raw + kMaxQueryTermsChunk;
     float* qw_raw = reinterpret_cast<float*>(seg_e_raw + kMaxQueryTermsChunk);
+    uint32_t* mw_s = reinterpret_cast<uint32_t*>(qw_raw + kMaxQueryTermsChunk);   // [R/32] eligibility words of the block
     __shared__ int cnt_s;
     __shared__ unsigned long long npost_s;
 
@@ -150,12 +151,17 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
 
     // ---- selection.  Keys are recomputed from the accumulators on each pass (keeps registers low -> more CTAs/SM).
     const uint32_t* m = p.masks != nullptr ? p.masks[q] : nullptr;
+    // the block's eligibility words go to shared memory once (R/32 words, coalesced); sel[] is free until the push
+    const bool use_mask = m != nullptr;
+    if (use_mask)
+        for (int i = tid; i < R / 32; i += NT) mw_s[i] = m[(size_t)b * (R / 32) + i];
+    __syncthreads();
     auto key_of = [&](int i) -> uint64_t {
         const int idx = i * NT + tid;
         const float v = acc[idx];
         const uint32_t doc = (uint32_t)b * (uint32_t)R + (uint32_t)idx;
         bool ok = __float_as_uint(v) != 0x80000000u;
-        if (ok && m != nullptr) ok = (m[doc >> 5] >> (doc & 31)) & 1u;
+        if (ok && use_mask) ok = (mw_s[idx >> 5] >> (idx & 31)) & 1u;
         return ok ? make_key(v, doc) : 0ull;
     };
     uint64_t tmax = 0;
@@ -236,7 +242,8 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_scan_kernel(const Spars
 
 template <int EPT>
 static int launch_scan_t(Shard* s, const SparseScanParams& p, int batch) {
-    const size_t smem = (size_t)EPT * kSparseThreads * 4 + (size_t)kSelCap * 8 + (size_t)kMaxQueryTermsChunk * 24;
+    const size_t smem = (size_t)EPT * kSparseThreads * 4 + (size_t)kSelCap * 8 + (size_t)kMaxQueryTermsChunk * 24 +
+                        (size_t)EPT * kSparseThreads / 8;
     auto kern = sparse_scan_kernel<EPT>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -1,0 +1,123 @@
+"""BASELINE.json configs on ONE GPU (full config where it fits one GPU, otherwise the per-GPU shard of the 8-GPU
+config), device-resident timing with CUDA events, JSON report for profiles/.
+
+    python tools/run_configs.py [--out gpurun_out/configs.json] [--only c2,c4]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "audio-rag_b200"), os.path.join(ROOT, "tools")]
+from b200rag import Shard, normalize_bf16, synth  # noqa: E402
+from probe import build_shard  # noqa: E402
+
+PEAK_HBM = 6464.9
+PEAK_TF = 1413.9
+try:
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    PEAK_HBM, PEAK_TF = pk["hbm_gbs"], pk["bf16_tflops_sustained"]
+except Exception:
+    pass
+
+
+def run(sh, dev, rows_total, mode, B, top_k, iters, mask_ids=None, label=""):
+    qf = synth.dense_queries_f32(2000, 0, B, rows_total, sh.dim, corpus_seed=1234)
+    ip, tt, ww = synth.sparse_queries(2000, 0, B)
+    qb = normalize_bf16(qf)
+    q, keep = sh.make_query(mode, top_k, qb, ip, tt, ww, mask_ids=mask_ids)
+    nlegs, L = Shard.legs_len(q)
+    cands = torch.zeros((nlegs * B * L + 1, 2), dtype=torch.int64, device=dev)
+    oi = torch.empty((B, top_k), dtype=torch.int64, device=dev)
+    osc = torch.empty((B, top_k), dtype=torch.float64, device=dev)
+    oc = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    sh.stage(q, keep)
+    for _ in range(3):
+        sh.legs(cands, cands[-1])
+        sh.fuse(cands, 1, oi, osc, oc, has_trailer=True)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        sh.legs(cands, cands[-1])
+        sh.fuse(cands, 1, oi, osc, oc, has_trailer=True)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    st = sh.stats()
+    p50 = ms[len(ms) // 2]
+    rows = sh.count
+    r = {"config": label, "mode": mode, "rows_on_gpu": rows, "batch": B, "top_k": top_k, "p50_ms": p50,
+         "queries_per_s": B / (p50 / 1e3), "dense_path": {0: None, 1: "simt_bulk_scan", 2: "tcgen05_gemm"}[st["dense_path"]],
+         "dense_passes": st["dense_passes"], "dense_scan_ms": st["dense_scan_ms"], "sparse_scan_ms": st["sparse_scan_ms"],
+         "sparse_postings": st["sparse_postings"], "kernel_launches": st["kernel_launches"],
+         "ambiguous": int(oc[B].item())}
+    if st["dense_scan_ms"] > 0:
+        gb = rows * sh.dim * 2 / 1e9
+        per_pass = st["dense_scan_ms"] / max(st["dense_passes"], 1)
+        r["dense_GBps_per_pass"] = gb / (per_pass / 1e3)
+        r["dense_hbm_frac"] = r["dense_GBps_per_pass"] / PEAK_HBM
+        r["dense_TFLOPs"] = 2.0 * B * rows * sh.dim / (st["dense_scan_ms"] / 1e3) / 1e12
+        r["dense_tensor_frac"] = r["dense_TFLOPs"] / PEAK_TF
+    if st["sparse_scan_ms"] > 0:
+        r["sparse_GBps"] = st["sparse_postings"] * 6 / 1e9 / (st["sparse_scan_ms"] / 1e3)
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
+    ap.add_argument("--only", default="c2,c3,c4,c5")
+    a = ap.parse_args()
+    only = a.only.split(",")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    res = []
+
+    def shard(n, sparse, n_total=None):
+        sh = build_shard(n, 1024, sparse, dev, n_total=n_total or n)
+        sh.set_profiling(True)
+        return sh
+
+    if "c2" in only:       # dense-only exact top-10 over 1M x 1024 bf16, B = 1 and 256, 1 x B200
+        sh = shard(1_000_000, False)
+        res.append(run(sh, dev, 1_000_000, "dense", 1, 10, 50, label="config2 dense top-10 1M B=1"))
+        res.append(run(sh, dev, 1_000_000, "dense", 256, 10, 30, label="config2 dense top-10 1M B=256"))
+        res.append(run(sh, dev, 1_000_000, "dense", 64, 10, 30, label="(extra) dense top-10 1M B=64"))
+        sh.close()
+        torch.cuda.empty_cache()
+    if "c3" in only:       # hybrid top-10 over 10M sharded over 8 GPUs: the per-GPU shard (1.25M rows)
+        sh = shard(1_250_000, True, n_total=10_000_000)
+        res.append(run(sh, dev, 10_000_000, "hybrid", 1, 10, 50, label="config3 hybrid top-10, per-GPU shard of 10M/8, B=1"))
+        if "c4" in only:   # multi-tenant, 1k collections, batch 64: per-GPU shard
+            thr = torch.from_numpy(synth.zipf_thresholds(1000).view(np.int64)).to(dev)
+            rng = np.random.default_rng(7)
+            colls = synth.row_collections(99, 0, 64, 1000)      # tenant of each query ~ Zipf like the rows
+            for i, c in enumerate(sorted(set(int(x) for x in colls))):
+                words = torch.zeros((sh.count + 31) // 32, dtype=torch.int32, device=dev)
+                sh.synth_collection_mask(1234, 0, sh.count, thr, 1000, c, words)
+                sh.mask_set(c, words, sh.count)
+            res.append(run(sh, dev, 10_000_000, "hybrid", 64, 10, 20, mask_ids=colls.astype(np.int32),
+                           label="config4 multi-tenant hybrid top-10, 1k-collection bitmask, per-GPU shard of 10M/8, B=64"))
+            res.append(run(sh, dev, 10_000_000, "hybrid", 64, 10, 20, label="(extra) same without masks, B=64"))
+        sh.close()
+        torch.cuda.empty_cache()
+    if "c5" in only:       # hybrid top-100 over 100M on 8 GPUs: the per-GPU shard (12.5M rows), B = 1 and 128
+        sh = shard(12_500_000, True, n_total=100_000_000)
+        res.append(run(sh, dev, 100_000_000, "hybrid", 1, 100, 10, label="config5 hybrid top-100, per-GPU shard of 100M/8, B=1"))
+        res.append(run(sh, dev, 100_000_000, "dense", 128, 100, 5, label="config5 dense leg top-100, per-GPU shard of 100M/8, B=128"))
+        sh.close()
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump({"peaks": {"hbm_gbs": PEAK_HBM, "bf16_tflops_sustained": PEAK_TF}, "results": res,
+               "note": "device-resident p50 per batch, CUDA events, one B200; sharded configs show ONE rank's work "
+                       "(the NCCL all-gather of candidates is measured by bench.py --gpus N)"}, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
