@@ -315,3 +315,22 @@ def test_hybrid_masks_gemm_path(gpu):
     _run_and_check(sh, c, "hybrid", 8, 10, masks=masks, mask_ids=mask_ids, batch=8)
     _run_and_check(sh, c, "dense", 8, 10, masks=masks, mask_ids=mask_ids, batch=4)
     sh.close()
+
+
+def test_large_topk_and_batches_all_paths(gpu):
+    """top-100 hybrid (Lc = 300: shared-memory candidate lists, several query passes), a batch above 128 queries, masks."""
+    from b200rag import synth
+    c = Corpus(25_000, dim=256, vocab=40_009)
+    sh = _shard_from(c, gpu, docs_per_block=4096)
+    coll = synth.row_collections(c.seed, 0, c.n, 3)
+    masks = {m: coll == m for m in range(3)}
+    for m in range(3):
+        sh.mask_set(m, synth.pack_mask(masks[m]), c.n)
+    for path in (0, 2):
+        sh.set_dense_path(path)
+        _run_and_check(sh, c, "hybrid", 5, 100, masks=masks, mask_ids=[0, 1, 2, -1, 0], batch=5)
+        _run_and_check(sh, c, "dense", 40, 100, batch=40, qid_start=10)
+    sh.set_dense_path(0)
+    _run_and_check(sh, c, "hybrid", 150, 10, batch=150, qid_start=300)
+    _run_and_check(sh, c, "sparse", 70, 20, batch=70, qid_start=500)
+    sh.close()
