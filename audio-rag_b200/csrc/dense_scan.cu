@@ -29,6 +29,8 @@ struct DenseScanParams {
     uint64_t* out;                 // [NQ][grid][Lc]
     int64_t out_q_stride;          // grid * Lc
     int Lc, cap, stages;
+    int interleave;
+    int split;
 };
 
 constexpr int kScanThreads = 32 + 32 * kScanConsumerWarps;
@@ -60,22 +62,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     }
     __syncthreads();
 
-    const int64_t t0 = p.n_tiles * (int64_t)blockIdx.x / (int64_t)gridDim.x;
-    const int64_t t1 = p.n_tiles * (int64_t)(blockIdx.x + 1) / (int64_t)gridDim.x;
+    // tile order: interleaved (tile t -> CTA t mod grid: all SMs sweep one contiguous window of the corpus together)
+    // or contiguous ranges per CTA
+    const int64_t t0 = p.interleave ? (int64_t)blockIdx.x : p.n_tiles * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+    const int64_t t1 = p.interleave ? p.n_tiles : p.n_tiles * (int64_t)(blockIdx.x + 1) / (int64_t)gridDim.x;
+    const int64_t tstep = p.interleave ? (int64_t)gridDim.x : 1;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
-            for (int64_t t = t0; t < t1; ++t) {
+            for (int64_t t = t0; t < t1; t += tstep) {
                 mbar_wait(&empty[st], ph ^ 1u);
                 const int64_t row0 = t * T;
                 const int64_t left = p.n_rows - row0;
                 const uint32_t rows = left < T ? (uint32_t)left : (uint32_t)T;
                 const uint32_t bytes = rows * ROW_BYTES;
                 mbar_arrive_expect_tx(&full[st], bytes);
-                bulk_g2s(ring + (size_t)st * STAGE_BYTES, p.corpus + row0 * DIM, bytes, &full[st]);
+                {
+                    // one stage = `split` bulk copies (all complete on the same barrier)
+                    const uint32_t piece = (uint32_t)STAGE_BYTES / (uint32_t)p.split;
+                    uint8_t* dst = ring + (size_t)st * STAGE_BYTES;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.corpus + row0 * DIM);
+                    for (uint32_t o = 0; o < bytes; o += piece)
+                        bulk_g2s(dst + o, src + o, bytes - o < piece ? bytes - o : piece, &full[st]);
+                }
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
 
     int st = 0;
     uint32_t ph = 0;
-    for (int64_t t = t0; t < t1; ++t) {
+    for (int64_t t = t0; t < t1; t += tstep) {
         // refresh from the grid-wide thresholds (monotone; any CTA's Lc-th best is a valid lower bound)
         uint64_t g[NQ];
 #pragma unroll
@@ -276,6 +288,8 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.Lc = Lc;
         p.cap = cap;
         p.stages = stages;
+        p.interleave = s->tile_interleave;
+        p.split = s->bulk_split;
 
         int rc;
         if (nq == 2) {

@@ -159,7 +159,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_TRY(s->ws.lists_b.ensure((size_t)B * nl_max * Lc * 8, 0, st));
             int nlists = 0;
             const bool use_gemm = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
-            s->dense_stage_cap = overlap ? 5 : s->dense_stage_cap_env;
+            s->dense_stage_cap = s->dense_stage_cap_env;   // (3 x 32 KB leaves room for a co-resident sparse CTA too)
             if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
             else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
             s->dense_stage_cap = 0;
@@ -281,6 +281,8 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_OVERLAP")) { s->overlap_legs = atoi(e) != 0; s->overlap_force = atoi(e) == 2; }
     if (const char* e = getenv("B200RAG_OVERLAP_MAX_ROWS")) s->overlap_max_rows = atoll(e);
     if (const char* e = getenv("B200RAG_DENSE_STAGES")) s->dense_stage_cap_env = atoi(e);
+    if (const char* e = getenv("B200RAG_TILE_INTERLEAVE")) s->tile_interleave = atoi(e);
+    if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }
     int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);
     if (rc == B200RAG_OK) {
         e = cudaMemsetAsync(s->fwd_ptr.p, 0, 8, s->stream);
