@@ -68,12 +68,37 @@ __device__ __forceinline__ void named_bar_sync(int bar_id, int nthreads) {
 }
 
 __device__ __forceinline__ void cta_bitonic_desc(uint64_t* keys, int n, int tid, int nthreads, int bar_id) {
+    // Compare distances j < 64 stay inside aligned 64-key chunks: a warp owns whole chunks and only needs __syncwarp
+    // there.  Only the j >= 64 steps cross warps and take a block barrier: 14 barriers instead of 55 for n = 1024.
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     named_bar_sync(bar_id, nthreads);
-    for (int k = 2; k <= n; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += nthreads) bitonic_step(keys, i, j, k);
-            named_bar_sync(bar_id, nthreads);
+    if (n < 64 || nwarps == 0) {
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n; i += nthreads) bitonic_step(keys, i, j, k);
+                named_bar_sync(bar_id, nthreads);
+            }
+        return;
+    }
+    const int nchunks = n >> 6;
+    for (int k = 2; k <= n; k <<= 1) {
+        int j = k >> 1;
+        if (j >= 64) {
+            named_bar_sync(bar_id, nthreads);          // warp-local results of the previous phase become visible
+            for (; j >= 64; j >>= 1) {
+                for (int i = tid; i < n; i += nthreads) bitonic_step(keys, i, j, k);
+                named_bar_sync(bar_id, nthreads);
+            }
         }
+        for (; j > 0; j >>= 1) {
+            for (int c = warp; c < nchunks; c += nwarps) {
+                bitonic_step(keys, (c << 6) + lane, j, k);
+                bitonic_step(keys, (c << 6) + 32 + lane, j, k);
+            }
+            __syncwarp();
+        }
+    }
+    named_bar_sync(bar_id, nthreads);
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -233,6 +233,9 @@ template <int NCH, int NQ>
 static int launch_one(Shard* s, const DenseScanParams& p, int grid, size_t smem) {
     auto kern = dense_scan_kernel<NCH, NQ>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // keep the SM's shared-memory carve-out at its maximum: the ring only needs ~105 KB, and the sparse leg's CTAs
+    // (side stream) are meant to co-reside in what is left
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<grid, kScanThreads, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
