@@ -5,13 +5,14 @@
 //
 // Shape: persistent grid of one CTA per SM.  Warp 0 is the producer: one elected lane streams 16-row tiles
 // (32 KB at 1024-d) of the bf16 corpus into a shared-memory ring with 1-D bulk async copies (TMA engine,
-// cp.async.bulk -> SASS UBLKCP) completing on mbarriers; 5-6 stages keep ~160-190 KB in flight per SM, well
-// above the ~35 KB Little's-law floor for HBM3e.  Warps 1-8 consume: each takes two rows of a tile, reads
-// them with conflict-free 128-bit LDS, multiplies against the query held in registers (fp32 FMA), butterfly-
-// reduces, and streams the score into a warp-private top-Lc selection (threshold + smem buffer + in-warp
-// bitonic compaction).  Thresholds are shared grid-wide through a monotone atomicMax so that after the
-// first few tiles almost no row passes the compare.  The score vector never reaches HBM; each CTA emits
-// one sorted list of Lc keys per query.
+// cp.async.bulk -> SASS UBLKCP) completing on mbarriers.  Measured on B200: a 3-stage ring filled in 8 KB pieces
+// (96 KB in flight per SM) reaches 6.7 TB/s, deeper rings are slower (6 stages: 6.2 TB/s).  Warps 1-8 consume: each
+// takes two rows of a tile, reads them with conflict-free 128-bit LDS, multiplies against the query held in
+// registers (fp32 FMA), butterfly-reduces, and streams the score into a warp-private top-Lc selection: a sorted
+// list spread over the warp's registers (ballot + shuffle insert) for Lc <= 64, else threshold + smem buffer +
+// in-warp bitonic compaction.  Thresholds are shared grid-wide through a monotone atomicMax so that after the
+// first few tiles almost no row passes the compare.  The score vector never reaches HBM; each CTA emits one sorted
+// list of Lc keys per query.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = n_rows * dim * 2.
 #include "common.cuh"
@@ -38,7 +39,12 @@ constexpr int kScanThreads = 32 + 32 * kScanConsumerWarps;
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-template <int NCH, int NQ>
+// LW > 0: each consumer warp keeps its running top list SORTED IN REGISTERS, spread over the lanes (entry i in lane
+//         i & 31, register i >> 5; LW = 32 or 64 slots >= Lc).  A score that beats the Lc-th entry is inserted with
+//         one ballot + one shuffle-shift: no shared memory, no compaction pauses, and the threshold is always the
+//         exact Lc-th best of the rows this warp has seen.
+// LW == 0: larger top-k: append to a shared-memory buffer, bitonic-compact when it fills.
+template <int NCH, int NQ, int LW>
 __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const DenseScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int T = kScanTileRows;
@@ -49,7 +55,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     uint8_t* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
     uint64_t* empty = full + p.stages;
-    uint64_t* bufs = empty + p.stages;  // [consumer warp][NQ][cap]
+    uint64_t* sthr = empty + p.stages;  // [stage][2] grid-wide thresholds sampled by the producer with each tile
+    uint64_t* bufs = sthr + 2 * p.stages;  // [consumer warp][NQ][cap]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -73,12 +80,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
+            uint64_t gcur[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) gcur[q] = 0;
             for (int64_t t = t0; t < t1; t += tstep) {
                 mbar_wait(&empty[st], ph ^ 1u);
                 const int64_t row0 = t * T;
                 const int64_t left = p.n_rows - row0;
                 const uint32_t rows = left < T ? (uint32_t)left : (uint32_t)T;
                 const uint32_t bytes = rows * ROW_BYTES;
+                // one volatile read of the grid-wide thresholds per tile per CTA, handed to the consumers with the
+                // stage (ordered by the barrier arrive below), instead of one read per consumer warp
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) sthr[st * 2 + q] = gcur[q];
                 mbar_arrive_expect_tx(&full[st], bytes);
                 {
                     // one stage = `split` bulk copies (all complete on the same barrier)
@@ -88,6 +102,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
                     for (uint32_t o = 0; o < bytes; o += piece)
                         bulk_g2s(dst + o, src + o, bytes - o < piece ? bytes - o : piece, &full[st]);
                 }
+                // sample for the NEXT tile now: the load's latency hides behind the wait for a free stage
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) gcur[q] = ld_volatile_u64(&p.g_thr[q]);
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
@@ -114,22 +131,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     uint64_t thr[NQ];
     int cnt[NQ];
     uint64_t* mybuf[NQ];
+    uint64_t e0[NQ], e1[NQ];          // LW > 0: my slots of the warp's sorted list (descending over lane, then register)
+    uint64_t lthr[NQ];                // LW > 0: the list's own Lc-th entry
+    bool dirty[NQ];
+    int tcount = 0;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         thr[q] = 0;
         cnt[q] = 0;
+        e0[q] = e1[q] = lthr[q] = 0;
+        dirty[q] = false;
         mybuf[q] = bufs + ((size_t)cw * NQ + q) * p.cap;
     }
 
     int st = 0;
     uint32_t ph = 0;
     for (int64_t t = t0; t < t1; t += tstep) {
-        // refresh from the grid-wide thresholds (monotone; any CTA's Lc-th best is a valid lower bound)
+        mbar_wait(&full[st], ph);
+        // refresh from the grid-wide thresholds (monotone; any warp's Lc-th best is a valid lower bound)
         uint64_t g[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) g[q] = ld_volatile_u64(&p.g_thr[q]);
-
-        mbar_wait(&full[st], ph);
+        for (int q = 0; q < NQ; ++q) g[q] = sthr[st * 2 + q];
         const uint8_t* sp = ring + (size_t)st * STAGE_BYTES;
         const int64_t row0 = t * T;
         const int64_t left = p.n_rows - row0;
@@ -188,7 +210,26 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
                     bool ok = true;
                     const uint32_t* m = p.masks[q];
                     if (m != nullptr) ok = (m[row >> 5] >> (row & 31)) & 1u;
-                    if (ok) {
+                    if (ok && LW > 0) {
+                        // position = number of entries that beat the key (they form a prefix: the list is sorted)
+                        const int p0 = 32 - __popc(__ballot_sync(0xffffffffu, key > e0[q]));
+                        const uint64_t up0 = __shfl_up_sync(0xffffffffu, e0[q], 1);
+                        if (LW > 32) {
+                            const int p1 = 32 - __popc(__ballot_sync(0xffffffffu, key > e1[q]));
+                            const uint64_t up1 = __shfl_up_sync(0xffffffffu, e1[q], 1);
+                            const uint64_t carry = __shfl_sync(0xffffffffu, e0[q], 31);
+                            if (p0 < 32) e1[q] = lane == 0 ? carry : up1;
+                            else e1[q] = lane > p1 ? up1 : (lane == p1 ? key : e1[q]);
+                        }
+                        if (p0 < 32) e0[q] = lane > p0 ? up0 : (lane == p0 ? key : e0[q]);
+                        const int li = p.Lc - 1;
+                        const uint64_t nt = __shfl_sync(0xffffffffu, (LW > 32 && li >= 32) ? e1[q] : e0[q], li & 31);
+                        if (nt > lthr[q]) {
+                            lthr[q] = nt;
+                            if (nt > thr[q]) thr[q] = nt;
+                            dirty[q] = true;      // published below, at most once every 8 tiles (one hot address)
+                        }
+                    } else if (ok) {
                         if (lane == 0) mybuf[q][cnt[q]] = key;
                         if (++cnt[q] == p.cap) {
                             warp_bitonic_desc(mybuf[q], p.cap, lane);
@@ -203,14 +244,24 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
                 }
             }
         }
+        if (LW > 0 && (++tcount & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (dirty[q]) {
+                    dirty[q] = false;
+                    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[q]), (unsigned long long)lthr[q]);
+                }
+        }
     }
 
-    // ---- per-warp final compaction, then one CTA-level merge per query (ring memory is free now)
+    // ---- per-warp final compaction (buffer flavour only), then one CTA-level merge per query (ring memory is free now)
+    if (LW == 0) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        __syncwarp();
-        for (int i = cnt[q] + lane; i < p.cap; i += 32) mybuf[q][i] = 0;
-        warp_bitonic_desc(mybuf[q], p.cap, lane);
+        for (int q = 0; q < NQ; ++q) {
+            __syncwarp();
+            for (int i = cnt[q] + lane; i < p.cap; i += 32) mybuf[q][i] = 0;
+            warp_bitonic_desc(mybuf[q], p.cap, lane);
+        }
     }
     uint64_t* marea = reinterpret_cast<uint64_t*>(ring);
     const int mcount = kScanConsumerWarps * p.Lc;
@@ -218,7 +269,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         named_bar_sync(1, NCT);  // every warp is past its last ring read / previous query's output
-        for (int i = lane; i < p.Lc; i += 32) marea[cw * p.Lc + i] = mybuf[q][i];
+        if (LW > 0) {
+            if (lane < p.Lc) marea[cw * p.Lc + lane] = e0[q];
+            if (LW > 32 && lane + 32 < p.Lc) marea[cw * p.Lc + 32 + lane] = e1[q];
+        } else {
+            for (int i = lane; i < p.Lc; i += 32) marea[cw * p.Lc + i] = mybuf[q][i];
+        }
         for (int i = mcount + ctid; i < mpow2; i += NCT) marea[i] = 0;
         cta_bitonic_desc(marea, mpow2, ctid, NCT, 1);
         uint64_t* o = p.out + (size_t)q * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
@@ -229,9 +285,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     }
 }
 
-template <int NCH, int NQ>
+template <int NCH, int NQ, int LW>
 static int launch_one(Shard* s, const DenseScanParams& p, int grid, size_t smem) {
-    auto kern = dense_scan_kernel<NCH, NQ>;
+    auto kern = dense_scan_kernel<NCH, NQ, LW>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // keep the SM's shared-memory carve-out at its maximum: the ring only needs ~105 KB, and the sparse leg's CTAs
     // (side stream) are meant to co-reside in what is left
@@ -251,7 +307,11 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
     *nlists = grid;
 
-    const int cap = next_pow2(Lc + 32) < 64 ? 64 : next_pow2(Lc + 32);
+    // register-resident lists (up to 64 candidates) measured ~2 % SLOWER than the buffer flavour at B = 1 on B200
+    // (same box, 10M rows: 3.32 vs 3.26 ms), so they stay behind a knob (B200RAG_SCAN_REGLIST=1)
+    int lw = 0;
+    if (s->scan_reglist) lw = Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0);
+    const int cap = lw ? 1 : (next_pow2(Lc + 32) < 64 ? 64 : next_pow2(Lc + 32));
     const size_t stage_bytes = (size_t)kScanTileRows * nch * 512;
     const size_t max_smem = 227 * 1024;
     const size_t merge_bytes = (size_t)next_pow2(kScanConsumerWarps * Lc) * 8;
@@ -275,7 +335,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         if (s->dense_stage_cap > 0 && stages > s->dense_stage_cap) stages = s->dense_stage_cap;
         while ((size_t)stages * stage_bytes < merge_bytes) ++stages;
         if (stages < 2) { set_error("dense_scan: top-k too large for shared memory"); return B200RAG_ERR_INVALID; }
-        const size_t smem = (size_t)stages * stage_bytes + (size_t)stages * 16 + buf_bytes;
+        const size_t smem = (size_t)stages * stage_bytes + (size_t)stages * 32 + buf_bytes;
         if (smem > max_smem) { set_error("dense_scan: shared memory budget exceeded"); return B200RAG_ERR_INVALID; }
 
         DenseScanParams p{};
@@ -295,21 +355,25 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.split = s->bulk_split;
 
         int rc;
+#define B2_SCAN_CASE(NCH_, NQ_)                                                             \
+    (lw == 32 ? launch_one<NCH_, NQ_, 32>(s, p, grid, smem)                                 \
+              : (lw == 64 ? launch_one<NCH_, NQ_, 64>(s, p, grid, smem) : launch_one<NCH_, NQ_, 0>(s, p, grid, smem)))
         if (nq == 2) {
             switch (nch) {
-                case 1: rc = launch_one<1, 2>(s, p, grid, smem); break;
-                case 2: rc = launch_one<2, 2>(s, p, grid, smem); break;
-                case 3: rc = launch_one<3, 2>(s, p, grid, smem); break;
-                default: rc = launch_one<4, 2>(s, p, grid, smem); break;
+                case 1: rc = B2_SCAN_CASE(1, 2); break;
+                case 2: rc = B2_SCAN_CASE(2, 2); break;
+                case 3: rc = B2_SCAN_CASE(3, 2); break;
+                default: rc = B2_SCAN_CASE(4, 2); break;
             }
         } else {
             switch (nch) {
-                case 1: rc = launch_one<1, 1>(s, p, grid, smem); break;
-                case 2: rc = launch_one<2, 1>(s, p, grid, smem); break;
-                case 3: rc = launch_one<3, 1>(s, p, grid, smem); break;
-                default: rc = launch_one<4, 1>(s, p, grid, smem); break;
+                case 1: rc = B2_SCAN_CASE(1, 1); break;
+                case 2: rc = B2_SCAN_CASE(2, 1); break;
+                case 3: rc = B2_SCAN_CASE(3, 1); break;
+                default: rc = B2_SCAN_CASE(4, 1); break;
             }
         }
+#undef B2_SCAN_CASE
         if (rc != B200RAG_OK) return rc;
         s->stats.dense_passes++;
         q += nq;

@@ -82,6 +82,7 @@ struct Shard {
     int dense_stage_cap_env = 3;          // measured on B200: 3 stages x 32 KB in 8 KB pieces beats deeper rings (6.7 vs 6.2 TB/s)
     int tile_interleave = 1;
     int bulk_split = 4;
+    int scan_reglist = 0;                 // knob: register-resident candidate lists in the SIMT scan (default: smem buffer)
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
