@@ -166,7 +166,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             uint64_t* approx = nullptr;
             B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
             B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
-            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f,
+            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr,
                                        q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, out, ambiguous));
         }
     }
@@ -176,16 +176,19 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) {
             B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), sst));
         } else {
-            const size_t need = (size_t)B * s->n_blocks * Lc * 8;
+            const int sp_lists = sparse_scan_nlists(s, B);
+            const size_t need = (size_t)B * sp_lists * Lc * 8;
             B2_TRY(s->ws.lists_c.ensure(need, 0, st));
             B2_TRY(s->ws.lists_d.ensure(need, 0, st));
             B2_TRY(s->ws.exact2.ensure((size_t)B * Lc * 8, 0, st));
+            B2_TRY(s->ws.q_eps.ensure((size_t)B * 8, 0, st));
+            B2_CUDA(cudaMemsetAsync(s->ws.q_eps.as<int32_t>() + B, 0x80, (size_t)B * 4, sst));   // thresholds: 0x80808080 < any score
             s->stream = sst;                                   // the launchers below enqueue on s->stream
-            int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>());
+            int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.q_eps.as<float>(), s->ws.q_eps.as<int>() + B);
             uint64_t* approx = nullptr;
-            if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, (int)s->n_blocks, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
+            if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, sp_lists, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
             if (rc == B200RAG_OK) rc = launch_rescore_sparse(s, B, Lc, approx, s->ws.exact2.as<uint64_t>());
-            if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 4e-5f, 0, 0.f, out, ambiguous);
+            if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
             s->stream = st;
             if (rc != B200RAG_OK) return rc;
         }
@@ -283,6 +286,8 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_DENSE_STAGES")) s->dense_stage_cap_env = atoi(e);
     if (const char* e = getenv("B200RAG_TILE_INTERLEAVE")) s->tile_interleave = atoi(e);
     if (const char* e = getenv("B200RAG_SCAN_REGLIST")) s->scan_reglist = atoi(e);
+    if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
+    if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }
     int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);
     if (rc == B200RAG_OK) {
@@ -309,7 +314,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     for (auto& kv : s->masks) kv.second.release();
     s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
     s->ws.exact.release(); s->ws.cands.release(); s->ws.out.release();
-    s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release();
+    s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release(); s->ws.q_eps.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (int i = 0; i < 4; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -419,6 +424,7 @@ int b200rag_clear(b200rag_shard* sp) {
     B2_TRY(use_device(s));
     B2_CUDA(cudaStreamSynchronize(s->stream));
     s->n_rows = 0; s->nnz = 0; s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0;
+    s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->h_blk_base.clear();
     s->staged = false;
     for (auto& kv : s->masks) kv.second.release();

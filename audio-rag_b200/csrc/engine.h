@@ -64,6 +64,7 @@ struct Workspace {
     DevBuf lists_c;       // second set for the sparse leg, which runs concurrently on the side stream
     DevBuf lists_d;
     DevBuf exact2;
+    DevBuf q_eps;         // [B] f32 absolute error bound of the sparse scan's approximate scores | [B] i32 grid-wide thresholds
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
 };
@@ -82,6 +83,8 @@ struct Shard {
     int dense_stage_cap_env = 3;          // measured on B200: 3 stages x 32 KB in 8 KB pieces beats deeper rings (6.7 vs 6.2 TB/s)
     int tile_interleave = 1;
     int bulk_split = 4;
+    int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
+    int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
     int scan_reglist = 0;                 // knob: register-resident candidate lists in the SIMT scan (default: smem buffer)
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
@@ -96,6 +99,8 @@ struct Shard {
     DevBuf fwd_ptr;    // i64 [n_rows+1]
     DevBuf fwd_terms;  // u32 [nnz]
     DevBuf fwd_w;      // f32 [nnz]
+    float w_absmax = 0.f;   // max |w| over the first wmax_nnz postings (bounds sparse scores: fixed-point scale of the scan)
+    int64_t wmax_nnz = 0;
 
     // block-major inverted index: block b covers local docs [b*R, (b+1)*R)
     int64_t built_rows = 0;  // rows covered by complete blocks + the trailing partial block as of last build
@@ -147,13 +152,16 @@ int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, ui
 int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact);
 // sort exact keys, apply threshold, slack guard, emit b200rag_cand [batch, L]
 int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
-                        float eps_abs, float eps_rel, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
+                        float eps_abs, float eps_rel, const float* eps_abs_q /*[batch] or null*/, int has_thr, float thr,
+                        b200rag_cand* out, int32_t* ambiguous);
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
                 int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts);
 
 // ---- sparse.cu -----------------------------------------------------------------------------------------
 int build_inverted(Shard* s);
-int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, n_blocks, Lc]*/);
+int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, float* q_eps /*[batch]*/,
+                       int* gthr /*[batch], preset to INT_MIN*/);
+int sparse_scan_nlists(const Shard* s, int batch);
 
 // ---- synth.cu ------------------------------------------------------------------------------------------
 int launch_synth_dense(cudaStream_t st, uint64_t seed, int64_t row0, int64_t n, int dim, uint16_t* out);

@@ -180,7 +180,8 @@ int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, u
 // ------------------------------------------------------------------------------------------------ finalize leg
 __global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __restrict__ approx,
                                                            const uint64_t* __restrict__ exact, int Lc, int L,
-                                                           int npow2, float eps_abs, float eps_rel, int has_thr,
+                                                           int npow2, float eps_abs, float eps_rel,
+                                                           const float* __restrict__ eps_abs_q, int has_thr,
                                                            float thr, int64_t row_base, b200rag_cand* __restrict__ out,
                                                            int32_t* __restrict__ ambiguous) {
     extern __shared__ __align__(16) uint64_t fkeys[];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __res
             if (!have_bound) {
                 atomicAdd(ambiguous, 1);  // fewer than L survivors although candidates were cut: widen
             } else {
-                const float eps = eps_abs + eps_rel * fmaxf(fabsf(a), fabsf(bound));
+                const float eps = eps_abs + (eps_abs_q != nullptr ? eps_abs_q[q] : 0.f) + eps_rel * fmaxf(fabsf(a), fabsf(bound));
                 if (a + eps >= bound) atomicAdd(ambiguous, 1);
             }
         }
@@ -225,11 +226,11 @@ __global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __res
 }
 
 int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
-                        float eps_abs, float eps_rel, int has_thr, float thr, b200rag_cand* out,
-                        int32_t* ambiguous) {
+                        float eps_abs, float eps_rel, const float* eps_abs_q, int has_thr, float thr,
+                        b200rag_cand* out, int32_t* ambiguous) {
     const int npow2 = next_pow2(Lc);
     finalize_leg_kernel<<<batch, 256, (size_t)npow2 * 8, s->stream>>>(approx, exact, Lc, L, npow2, eps_abs, eps_rel,
-                                                                      has_thr, thr, s->cfg.row_base, out, ambiguous);
+                                                                      eps_abs_q, has_thr, thr, s->cfg.row_base, out, ambiguous);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;
