@@ -250,7 +250,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (cfg->dim <= 0 || cfg->dim % 256 != 0 || cfg->dim > 1024) { set_error("shard_create: dim must be a multiple of 256, <= 1024"); return B200RAG_ERR_INVALID; }
     if (cfg->vocab <= 0) { set_error("shard_create: vocab must be positive"); return B200RAG_ERR_INVALID; }
     int R = cfg->docs_per_block == 0 ? 8192 : cfg->docs_per_block;
-    if (R < 1024 || R > 32768 || (R & (R - 1)) != 0) { set_error("shard_create: docs_per_block must be a power of two in [1024, 32768]"); return B200RAG_ERR_INVALID; }
+    if (R < 1024 || R > 16384 || (R & (R - 1)) != 0) { set_error("shard_create: docs_per_block must be a power of two in [1024, 16384]"); return B200RAG_ERR_INVALID; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {

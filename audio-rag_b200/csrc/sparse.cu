@@ -79,14 +79,22 @@ __device__ __forceinline__ void sparse_scale(float qabs, float w_absmax, int nte
 // documents; a thread owns 8 consecutive postings, so at each step the 32 lanes of a warp would hit documents 8 apart:
 // 4 distinct banks, an 8-way conflict on every shared-memory atomic (ncu: 4.4 wavefronts per ATOMS).  Folding bits 5..9
 // into the bank bits makes every power-of-two stride up to 32 conflict-free.  The map is an involution that keeps
-// bits >= 5, so a slot's eligibility word is still word (slot >> 5).  post_doc stores the SLOT (applied at build time).
+// bits >= 5, so a slot's eligibility word is still word (slot >> 5).  post_doc stores 4 * SLOT, the byte offset of the
+// accumulator (applied at build time; docs_per_block <= 16384 keeps it in 16 bits).
 __host__ __device__ __forceinline__ uint32_t swz_doc(uint32_t d) { return d ^ ((d >> 5) & 31u); }
 
 // One CTA scans `bpc` consecutive blocks for one query and keeps a running candidate list across them, so its
 // pruning threshold strengthens block after block (and is shared grid-wide through gthr[q], like the dense scan):
 // in steady state a block's selection is ONE pass over the accumulators with almost nothing pushed.
+// 256-bit global load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 template <int NT, int EPT, int U, bool MASKED>
-__global__ void __launch_bounds__(NT) sparse_scan_kernel(const SparseScanParams p) {
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) sparse_scan_kernel(const SparseScanParams p) {
     extern __shared__ __align__(16) uint8_t ssm[];
     constexpr int R = EPT * NT;
     constexpr int kChunk = NT;      // query terms per pass: one term per thread
@@ -130,10 +138,11 @@ __global__ void __launch_bounds__(NT) sparse_scan_kernel(const SparseScanParams 
     sparse_scale(qabs_s, p.w_absmax, nterms, &cb, &S);
     if (g == 0 && tid == 0 && p.q_eps != nullptr) p.q_eps[q] = (float)nterms / S + 2.4e-7f * qabs_s * p.w_absmax;
     const float invS = 1.0f / S;
-    const uint32_t ucmul = 1u << cb;
+    uint32_t ucmul = 1u << cb;
     const int cmask = (int)ucmul - 1;
     constexpr float kMagic = 12582912.0f;                  // 1.5 * 2^23, bit pattern 0x4B400000
-    const uint32_t ucadd = 1u - 0x4B400000u * ucmul;       // (bits - 0x4B400000) * 2^cb + 1 == bits * 2^cb + ucadd (mod 2^32)
+    uint32_t ucadd = 1u - 0x4B400000u * ucmul;             // (bits - 0x4B400000) * 2^cb + 1 == bits * 2^cb + ucadd (mod 2^32)
+    asm volatile("" : "+r"(ucmul), "+r"(ucadd));           // opaque: one IMAD per posting instead of VIADD + SHF + VIADD
 
     // single-chunk queries (the common case) keep their term and weight in registers across blocks and prefetch the
     // next block's directory entries while the current block streams
@@ -257,8 +266,7 @@ __global__ void __launch_bounds__(NT) sparse_scan_kernel(const SparseScanParams 
                         const uint32_t ss = seg_s[j];
                         const uint32_t vec = (ss >> 3) + (v - pref[j]);
                         d4[u] = pd[vec];
-                        wa[u] = pw[2 * (size_t)vec];
-                        wb[u] = pw[2 * (size_t)vec + 1];
+                        ldg256(pw + 2 * (size_t)vec, wa[u], wb[u]);   // one 32-byte load: 8 wavefronts per warp instead of 2 x 8
                         lo[u] = ss; hi[u] = seg_e[j]; P[u] = vec << 3; wq[u] = qw[j];
                     }
                 }
@@ -270,16 +278,18 @@ __global__ void __launch_bounds__(NT) sparse_scan_kernel(const SparseScanParams 
                     if (P[u] >= lo[u] && P[u] + 8 <= hi[u]) {   // interior vector: all 8 postings belong to the segment
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const uint32_t d = (k & 1) ? (dd[k >> 1] >> 16) : (dd[k >> 1] & 0xFFFFu);
-                            atomicAdd(&acc[d], (int)(__float_as_uint(fmaf(wq[u], ww[k], kMagic)) * ucmul + ucadd));
+                            const uint32_t off = (k & 1) ? (dd[k >> 1] >> 16) : (dd[k >> 1] & 0xFFFFu);   // 4 * slot
+                            atomicAdd(reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(acc) + off),
+                                      (int)(__float_as_uint(fmaf(wq[u], ww[k], kMagic)) * ucmul + ucadd));
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const uint32_t Pk = P[u] + k;
                             if (Pk >= lo[u] && Pk < hi[u]) {
-                                const uint32_t d = (k & 1) ? (dd[k >> 1] >> 16) : (dd[k >> 1] & 0xFFFFu);
-                                atomicAdd(&acc[d], (int)(__float_as_uint(fmaf(wq[u], ww[k], kMagic)) * ucmul + ucadd));
+                                const uint32_t off = (k & 1) ? (dd[k >> 1] >> 16) : (dd[k >> 1] & 0xFFFFu);
+                                atomicAdd(reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(acc) + off),
+                                          (int)(__float_as_uint(fmaf(wq[u], ww[k], kMagic)) * ucmul + ucadd));
                             }
                         }
                     }
@@ -496,7 +506,7 @@ __global__ void unpack_block_kernel(const uint64_t* __restrict__ vals, int64_t c
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < cnt) {
         const uint64_t v = vals[i];
-        post_doc[base + i] = (uint16_t)swz_doc((uint32_t)(v >> 32));
+        post_doc[base + i] = (uint16_t)(4u * swz_doc((uint32_t)(v >> 32)));   // byte offset of the accumulator slot
         post_w[base + i] = __uint_as_float((uint32_t)v);
     } else if (i < padded) {
         post_doc[base + i] = 0;

@@ -48,7 +48,7 @@ typedef struct {
     int32_t device;         /* CUDA ordinal                                                             */
     int32_t dim;            /* embedding_dim (qdrant.py:24,99): multiple of 256, <= 1024                  */
     int32_t vocab;          /* sparse index space (XLM-R ids from BGE-M3, embeddings/bge.py:95-102)        */
-    int32_t docs_per_block; /* doc-range block of the inverted index: power of two, 1024..32768 (0 = 8192) */
+    int32_t docs_per_block; /* doc-range block of the inverted index: power of two, 1024..16384 (0 = 8192) */
     int64_t row_base;       /* global id of local row 0                                                  */
     int64_t reserve_rows;   /* optional pre-allocation hints (0 = grow on demand)                        */
     int64_t reserve_postings;
