@@ -39,12 +39,17 @@ constexpr int kScanThreads = 32 + 32 * kScanConsumerWarps;
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-// LW > 0: each consumer warp keeps its running top list SORTED IN REGISTERS, spread over the lanes (entry i in lane
-//         i & 31, register i >> 5; LW = 32 or 64 slots >= Lc).  A score that beats the Lc-th entry is inserted with
-//         one ballot + one shuffle-shift: no shared memory, no compaction pauses, and the threshold is always the
-//         exact Lc-th best of the rows this warp has seen.
-// LW == 0: larger top-k: append to a shared-memory buffer, bitonic-compact when it fills.
-template <int NCH, int NQ, int LW>
+// SH == 0: every consumer warp appends to its own shared-memory buffer and bitonic-compacts it when it fills (cheap for
+//          small top-k: 64-key buffers).
+// SH == 1: larger top-k: ONE buffer per CTA and query.  A warp-private 512-key compaction takes ~10 us during which the
+//          warp's two rows of every tile are not consumed, so the whole ring stalls (measured: top-100 scans at 4.6-5.4
+//          TB/s instead of 6.3).  The shared buffer sees 8x the rows, so its threshold is 8x tighter (5x fewer pushes),
+//          and all 8 warps sort it together.  Consumers meet at a named barrier every kSyncTiles tiles; the decision to
+//          compact is taken one interval ahead by one thread, so every warp sees the same decision.
+constexpr int kSyncTiles = 8;
+constexpr int kSharedMargin = 2 * kSyncTiles * kScanTileRows;   // pushes possible between decision and compaction
+
+template <int NCH, int NQ, int SH>
 __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const DenseScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int T = kScanTileRows;
@@ -56,7 +61,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
     uint64_t* empty = full + p.stages;
     uint64_t* sthr = empty + p.stages;  // [stage][2] grid-wide thresholds sampled by the producer with each tile
-    uint64_t* bufs = sthr + 2 * p.stages;  // [consumer warp][NQ][cap]
+    uint64_t* bufs = sthr + 2 * p.stages;  // SH == 0: [consumer warp][NQ][cap];  SH == 1: [NQ][cap] | cthr[NQ] | ccnt[NQ] | flag[NQ]
+    uint64_t* cthr = bufs + (size_t)NQ * p.cap;
+    int* ccnt = reinterpret_cast<int*>(cthr + NQ);
+    int* cflag = ccnt + NQ;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -66,6 +74,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
             mbar_init(&empty[s], kScanConsumerWarps);
         }
         fence_mbar_init();
+        if (SH) {
+            for (int q = 0; q < NQ; ++q) { cthr[q] = 0; ccnt[q] = 0; cflag[q] = 0; }
+        }
     }
     __syncthreads();
 
@@ -131,18 +142,30 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     uint64_t thr[NQ];
     int cnt[NQ];
     uint64_t* mybuf[NQ];
-    uint64_t e0[NQ], e1[NQ];          // LW > 0: my slots of the warp's sorted list (descending over lane, then register)
-    uint64_t lthr[NQ];                // LW > 0: the list's own Lc-th entry
-    bool dirty[NQ];
     int tcount = 0;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         thr[q] = 0;
         cnt[q] = 0;
-        e0[q] = e1[q] = lthr[q] = 0;
-        dirty[q] = false;
-        mybuf[q] = bufs + ((size_t)cw * NQ + q) * p.cap;
+        mybuf[q] = SH ? bufs + (size_t)q * p.cap : bufs + ((size_t)cw * NQ + q) * p.cap;
     }
+
+    // SH: sort the CTA's buffer of query q (all consumer warps), keep the best Lc, publish the new threshold
+    auto compact_shared = [&](int q) {
+        const int n = ccnt[q];
+        named_bar_sync(1, NCT);
+        for (int i = n + ctid; i < p.cap; i += NCT) mybuf[q][i] = 0;
+        cta_bitonic_desc(mybuf[q], p.cap, ctid, NCT, 1);
+        if (ctid == 0) {
+            if (n > p.Lc) ccnt[q] = p.Lc;
+            const uint64_t nt = mybuf[q][p.Lc - 1];
+            if (nt > cthr[q]) {
+                cthr[q] = nt;
+                atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[q]), (unsigned long long)nt);
+            }
+        }
+        named_bar_sync(1, NCT);
+    };
 
     int st = 0;
     uint32_t ph = 0;
@@ -210,24 +233,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
                     bool ok = true;
                     const uint32_t* m = p.masks[q];
                     if (m != nullptr) ok = (m[row >> 5] >> (row & 31)) & 1u;
-                    if (ok && LW > 0) {
-                        // position = number of entries that beat the key (they form a prefix: the list is sorted)
-                        const int p0 = 32 - __popc(__ballot_sync(0xffffffffu, key > e0[q]));
-                        const uint64_t up0 = __shfl_up_sync(0xffffffffu, e0[q], 1);
-                        if (LW > 32) {
-                            const int p1 = 32 - __popc(__ballot_sync(0xffffffffu, key > e1[q]));
-                            const uint64_t up1 = __shfl_up_sync(0xffffffffu, e1[q], 1);
-                            const uint64_t carry = __shfl_sync(0xffffffffu, e0[q], 31);
-                            if (p0 < 32) e1[q] = lane == 0 ? carry : up1;
-                            else e1[q] = lane > p1 ? up1 : (lane == p1 ? key : e1[q]);
-                        }
-                        if (p0 < 32) e0[q] = lane > p0 ? up0 : (lane == p0 ? key : e0[q]);
-                        const int li = p.Lc - 1;
-                        const uint64_t nt = __shfl_sync(0xffffffffu, (LW > 32 && li >= 32) ? e1[q] : e0[q], li & 31);
-                        if (nt > lthr[q]) {
-                            lthr[q] = nt;
-                            if (nt > thr[q]) thr[q] = nt;
-                            dirty[q] = true;      // published below, at most once every 8 tiles (one hot address)
+                    if (ok && SH) {
+                        if (lane == 0) {
+                            const int pos = atomicAdd(&ccnt[q], 1);   // room is guaranteed by the margin (see below)
+                            mybuf[q][pos] = key;
                         }
                     } else if (ok) {
                         if (lane == 0) mybuf[q][cnt[q]] = key;
@@ -244,24 +253,41 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
                 }
             }
         }
-        if (LW > 0 && (++tcount & 7) == 0) {
+        if (SH && (++tcount & (kSyncTiles - 1)) == 0) {
+            // Every consumer warp has processed the same tiles.  cflag was written by one thread BEFORE this barrier (at
+            // the previous meeting), so all warps read the same decision; pushes that race with the decision are
+            // covered by the margin: a buffer is compacted while it still has >= kSharedMargin / 2 free slots.
+            named_bar_sync(1, NCT);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (dirty[q]) {
-                    dirty[q] = false;
-                    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[q]), (unsigned long long)lthr[q]);
-                }
+            for (int q = 0; q < NQ; ++q) {
+                if (cflag[q]) compact_shared(q);
+                const uint64_t ct = cthr[q];
+                if (ct > thr[q]) thr[q] = ct;
+            }
+            named_bar_sync(1, NCT);
+            if (ctid == 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) cflag[q] = ccnt[q] > p.cap - kSharedMargin ? 1 : 0;
+            }
         }
     }
 
-    // ---- per-warp final compaction (buffer flavour only), then one CTA-level merge per query (ring memory is free now)
-    if (LW == 0) {
+    if constexpr (SH != 0) {
+        // one sorted list per query straight from the CTA's buffer
+        named_bar_sync(1, NCT);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            __syncwarp();
-            for (int i = cnt[q] + lane; i < p.cap; i += 32) mybuf[q][i] = 0;
-            warp_bitonic_desc(mybuf[q], p.cap, lane);
+            compact_shared(q);
+            uint64_t* o = p.out + (size_t)q * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+            for (int i = ctid; i < p.Lc; i += NCT) o[i] = mybuf[q][i];
         }
+    } else {
+    // ---- per-warp final compaction, then one CTA-level merge per query (ring memory is free now)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        __syncwarp();
+        for (int i = cnt[q] + lane; i < p.cap; i += 32) mybuf[q][i] = 0;
+        warp_bitonic_desc(mybuf[q], p.cap, lane);
     }
     uint64_t* marea = reinterpret_cast<uint64_t*>(ring);
     const int mcount = kScanConsumerWarps * p.Lc;
@@ -269,12 +295,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         named_bar_sync(1, NCT);  // every warp is past its last ring read / previous query's output
-        if (LW > 0) {
-            if (lane < p.Lc) marea[cw * p.Lc + lane] = e0[q];
-            if (LW > 32 && lane + 32 < p.Lc) marea[cw * p.Lc + 32 + lane] = e1[q];
-        } else {
-            for (int i = lane; i < p.Lc; i += 32) marea[cw * p.Lc + i] = mybuf[q][i];
-        }
+        for (int i = lane; i < p.Lc; i += 32) marea[cw * p.Lc + i] = mybuf[q][i];
         for (int i = mcount + ctid; i < mpow2; i += NCT) marea[i] = 0;
         cta_bitonic_desc(marea, mpow2, ctid, NCT, 1);
         uint64_t* o = p.out + (size_t)q * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
@@ -283,11 +304,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
         if (ctid == 0 && marea[p.Lc - 1] != 0)
             atomicMax(reinterpret_cast<unsigned long long*>(&p.g_thr[q]), (unsigned long long)marea[p.Lc - 1]);
     }
+    }
 }
 
-template <int NCH, int NQ, int LW>
+template <int NCH, int NQ, int SH>
 static int launch_one(Shard* s, const DenseScanParams& p, int grid, size_t smem) {
-    auto kern = dense_scan_kernel<NCH, NQ, LW>;
+    auto kern = dense_scan_kernel<NCH, NQ, SH>;
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // keep the SM's shared-memory carve-out at its maximum: the ring only needs ~105 KB, and the sparse leg's CTAs
     // (side stream) are meant to co-reside in what is left
@@ -307,14 +329,12 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
     *nlists = grid;
 
-    // register-resident lists (up to 64 candidates) measured ~2 % SLOWER than the buffer flavour at B = 1 on B200
-    // (same box, 10M rows: 3.32 vs 3.26 ms), so they stay behind a knob (B200RAG_SCAN_REGLIST=1)
-    int lw = 0;
-    if (s->scan_reglist) lw = Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0);
-    const int cap = lw ? 1 : (next_pow2(Lc + 32) < 64 ? 64 : next_pow2(Lc + 32));
+    // selection flavour: one CTA-shared buffer (default) or warp-private buffers (knob: B200RAG_SCAN_SHARED=0)
+    const bool sh = s->scan_shared != 0;   // measured on B200 (10M rows): shared beats warp-private at every top-k (top-10: 3.18 vs 3.30 ms, top-100: 3.25 vs 3.95 ms)
+    const int cap = sh ? next_pow2(Lc + kSharedMargin + 64) : (next_pow2(Lc + 32) < 64 ? 64 : next_pow2(Lc + 32));
     const size_t stage_bytes = (size_t)kScanTileRows * nch * 512;
     const size_t max_smem = 227 * 1024;
-    const size_t merge_bytes = (size_t)next_pow2(kScanConsumerWarps * Lc) * 8;
+    const size_t merge_bytes = sh ? 0 : (size_t)next_pow2(kScanConsumerWarps * Lc) * 8;
 
     const uint64_t* thr_base = s->ws.thr.as<uint64_t>();
     (void)thr_base;
@@ -325,10 +345,10 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     int q = 0;
     while (q < batch) {
         int nq = (batch - q >= 2) ? 2 : 1;
-        size_t buf_bytes = (size_t)kScanConsumerWarps * nq * cap * 8;
+        size_t buf_bytes = sh ? (size_t)nq * cap * 8 + 64 : (size_t)kScanConsumerWarps * nq * cap * 8;
         if (nq == 2 && buf_bytes + 2 * stage_bytes + 256 > max_smem) {
             nq = 1;
-            buf_bytes = (size_t)kScanConsumerWarps * cap * 8;
+            buf_bytes = sh ? (size_t)cap * 8 + 64 : (size_t)kScanConsumerWarps * cap * 8;
         }
         int stages = (int)((max_smem - buf_bytes - 256) / stage_bytes);
         if (stages > 8) stages = 8;
@@ -355,9 +375,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.split = s->bulk_split;
 
         int rc;
-#define B2_SCAN_CASE(NCH_, NQ_)                                                             \
-    (lw == 32 ? launch_one<NCH_, NQ_, 32>(s, p, grid, smem)                                 \
-              : (lw == 64 ? launch_one<NCH_, NQ_, 64>(s, p, grid, smem) : launch_one<NCH_, NQ_, 0>(s, p, grid, smem)))
+#define B2_SCAN_CASE(NCH_, NQ_) (sh ? launch_one<NCH_, NQ_, 1>(s, p, grid, smem) : launch_one<NCH_, NQ_, 0>(s, p, grid, smem))
         if (nq == 2) {
             switch (nch) {
                 case 1: rc = B2_SCAN_CASE(1, 2); break;

@@ -85,7 +85,7 @@ struct Shard {
     int bulk_split = 4;
     int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
     int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
-    int scan_reglist = 0;                 // knob: register-resident candidate lists in the SIMT scan (default: smem buffer)
+    int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
