@@ -52,6 +52,10 @@ struct GemmParams {
     int64_t out_q_stride;          // grid * Lc
     int Lc;
     int stages;                    // pipeline depth actually used (2..kGemmStages), set by the launcher
+    int tile_stride;               // 1 = every 256-row tile; 16 = the sample pass (tiles 0, 16, 32, ...)
+    uint64_t* pool;                // filter mode: [batch][pool_cap] keys at or above the query's fixed threshold
+    int* pool_cnt;                 // filter mode: [batch] append counters (may exceed pool_cap: overflow is detected later)
+    int pool_cap;
     float* dbg_scores;             // optional [batch][n_rows] raw approximate scores (tests)
 };
 
@@ -145,6 +149,10 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGe
 //           threshold is the LREG-th best, slightly weaker than the Lc-th, which only admits a few more inserts).
 //           A sorted insert is LREG independent compare/selects: no memory, no dependent chain.
 // LREG == 0: lists live in shared memory (unsorted, replace-min) for large top-k.
+// LREG < 0:  FILTER mode, no lists at all: g_thr[q] holds a FIXED threshold (the K_s-th best score of a 1/16 sample of
+//            the shard, see launch_dense_gemm_filtered); every score at or above it is appended to the query's pool in
+//            global memory (~16 K_s keys per query over the whole shard).  The epilogue carries no per-query state
+//            besides one register, so 128 queries per pass fit whatever the top-k (smem lists: 32 at top-100).
 template <int LREG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
@@ -191,7 +199,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     uint8_t* sa = gsm + (size_t)st * kStageBytes;
                     mbar_arrive_expect_tx(&full[st], kStageBytes);
                     tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
-                    tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * kGemmN));
+                    tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * p.tile_stride * kGemmN));
                     if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
@@ -254,7 +262,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             // eligibility of the tile's 256 rows for my query = 8 consecutive words: pull their line towards L1 now,
             // read one word per chunk below
-            if (mask != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + t * (kGemmN / 32)));
+            const int64_t tt = t * p.tile_stride;          // the corpus tile this iteration scores
+            if (mask != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + tt * (kGemmN / 32)));
             mbar_wait(&tfull[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kGemmN);
@@ -263,7 +272,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
                 if (!warp_active) continue;
-                const int64_t row0 = t * kGemmN + c * 32;
+                const int64_t row0 = tt * kGemmN + c * 32;
                 if (p.dbg_scores != nullptr && active) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -277,7 +286,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         cm |= ((__uint_as_float(v[j]) + 0.0f >= thr_s) && j < nvalid) ? (1u << j) : 0u;
-                    if (mask != nullptr) cm &= __ldg(mask + t * (kGemmN / 32) + c);
+                    if (mask != nullptr) cm &= __ldg(mask + tt * (kGemmN / 32) + c);
                 }
                 if (!__any_sync(0xffffffffu, cm != 0)) continue;
                 // phase B (rare after warm-up): stage the chunk's scores, then insert survivors
@@ -292,8 +301,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         cm &= cm - 1;
                         const int64_t row = row0 + j;
                         const uint64_t key = make_key(stg[lane * 33 + j], (uint32_t)row);
-                        const bool ok = key > thr;               // (eligibility was applied to cm already)
-                        if (ok) {
+                        const bool ok = LREG < 0 ? key >= thr : key > thr;   // (eligibility was applied to cm already)
+                        if constexpr (LREG < 0) {
+                            if (ok) {
+                                const int pos = atomicAdd(&p.pool_cnt[qi], 1);
+                                if (pos < p.pool_cap) p.pool[(size_t)qi * p.pool_cap + pos] = key;
+                            }
+                        } else if (ok) {
                             if constexpr (LREG > 0) {
                                 // sorted insert (descending), every element decided from OLD neighbours: no chain
 #pragma unroll
@@ -330,7 +344,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 for (int i = 0; i < LREG; ++i)
                     if (i < p.Lc) o[i] = L[i];
             }
-        } else if (warp_active) {
+        } else if (LREG == 0 && warp_active) {
             // unsorted lists -> global [q][cta][Lc]; the merge tree sorts (it never assumes order)
             for (int ql = 0; ql < 32; ++ql) {
                 const int q = quad * 32 + ql;
@@ -398,17 +412,22 @@ static int launch_gemm_t(Shard* s, const CUtensorMap& map_q, const CUtensorMap& 
     return B200RAG_OK;
 }
 
-int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores) {
-    const int64_t n_tiles = (s->n_rows + kGemmN - 1) / kGemmN;
+// One or more corpus passes of <= 128 queries each.  tile_stride > 1 scores only every tile_stride-th 256-row tile (the
+// sample pass); pool != nullptr selects the filter epilogue (no lists: out_lists unused).
+static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores, int tile_stride,
+                       uint64_t* pool, int* pool_cnt, int pool_cap) {
+    const int64_t all_tiles = (s->n_rows + kGemmN - 1) / kGemmN;
+    const int64_t n_tiles = (all_tiles + tile_stride - 1) / tile_stride;
     int grid = s->sm_count;
     if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
-    *nlists = grid;
-    const int lreg = Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0);
+    if (nlists != nullptr) *nlists = grid;
+    const bool filter = pool != nullptr;
+    const int lreg = filter ? -1 : (Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0));
     // shared memory: S pipeline stages (48 KB each) + score staging (+ one list of Lc keys per query when the lists
     // do not fit in registers)
     const size_t max_smem = 227 * 1024, fixed = 1024 + 512 + 4 * 32 * 33 * 4;
     const int Lp = (Lc + 1) & ~1;
-    const size_t per_q = lreg ? 0 : (size_t)Lp * 8;
+    const size_t per_q = lreg != 0 ? 0 : (size_t)Lp * 8;
     int qpp = kGemmM;                                   // queries per pass
     while (qpp > 32 && fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) qpp -= 32;
     if (fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) {
@@ -417,9 +436,6 @@ int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     }
     CUtensorMap map_c;
     B2_TRY(make_map(&map_c, s->dense.p, s->n_rows, s->dim, kGemmN));
-    s->stats.dense_path = 2;
-    s->stats.dense_passes = 0;
-    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
     for (int q0 = 0; q0 < batch; q0 += qpp) {
         const int nq = batch - q0 < qpp ? batch - q0 : qpp;
         const size_t list_bytes = (size_t)((nq + 31) / 32 * 32) * per_q;
@@ -436,18 +452,104 @@ int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.batch = nq;
         p.masks = s->h_masks.empty() ? nullptr : s->ws.q_masks.as<const uint32_t*>() + q0;
         p.g_thr = s->ws.thr.as<uint64_t>() + q0;
-        p.out = out_lists + (size_t)q0 * grid * Lc;
+        p.out = filter ? nullptr : out_lists + (size_t)q0 * grid * Lc;
         p.out_q_stride = (int64_t)grid * Lc;
         p.Lc = Lc;
         p.stages = stages;
+        p.tile_stride = tile_stride;
+        p.pool = filter ? pool + (size_t)q0 * pool_cap : nullptr;
+        p.pool_cnt = filter ? pool_cnt + q0 : nullptr;
+        p.pool_cap = pool_cap;
         p.dbg_scores = dbg_scores != nullptr ? dbg_scores + (size_t)q0 * s->n_rows : nullptr;
-        if (lreg == 32) B2_TRY(launch_gemm_t<32>(s, map_q, map_c, p, grid, smem));
+        if (lreg < 0) B2_TRY(launch_gemm_t<-1>(s, map_q, map_c, p, grid, smem));
+        else if (lreg == 32) B2_TRY(launch_gemm_t<32>(s, map_q, map_c, p, grid, smem));
         else if (lreg == 64) B2_TRY(launch_gemm_t<64>(s, map_q, map_c, p, grid, smem));
         else B2_TRY(launch_gemm_t<0>(s, map_q, map_c, p, grid, smem));
         s->stats.kernel_launches++;
-        s->stats.dense_passes++;
+        if (tile_stride == 1) s->stats.dense_passes++;
     }
+    return B200RAG_OK;
+}
+
+int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores) {
+    s->stats.dense_path = 2;
+    s->stats.dense_passes = 0;
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
+    B2_TRY(gemm_passes(s, batch, Lc, out_lists, nlists, dbg_scores, 1, nullptr, nullptr, 0));
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[1], s->stream)); s->ev_dense = true; }
+    s->stats.dense_bytes = (int64_t)s->stats.dense_passes * s->n_rows * s->dim * 2;
+    return B200RAG_OK;
+}
+
+// ---- large top-k with query batches: sample pass -> fixed thresholds -> filter pass -> pool selection -------------
+constexpr int kSampleStride = 16;
+
+__global__ void set_filter_thr_kernel(const uint64_t* __restrict__ merged, int Ks, uint64_t* __restrict__ g_thr,
+                                      int* __restrict__ pool_cnt, int batch) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= batch) return;
+    g_thr[q] = merged[(size_t)q * Ks + Ks - 1];   // 0 while the sample holds fewer than Ks eligible rows: accept everything
+    pool_cnt[q] = 0;
+}
+
+// one CTA per query: sort the pool, emit the best Lc keys; flag the search as ambiguous (-> robust retry) when the
+// fixed threshold turned out too high (fewer than Lc rows passed although a threshold was applied) or the pool overflowed
+__global__ void __launch_bounds__(512) pool_select_kernel(const uint64_t* __restrict__ pool,
+                                                          const int* __restrict__ pool_cnt, int cap,
+                                                          const uint64_t* __restrict__ g_thr, int Lc,
+                                                          uint64_t* __restrict__ approx, int32_t* __restrict__ ambiguous) {
+    extern __shared__ __align__(16) uint64_t pkeys[];
+    const int q = blockIdx.x;
+    const int cnt = pool_cnt[q];
+    const int n = cnt < cap ? cnt : cap;
+    int npow2 = next_pow2(n > Lc ? n : Lc);
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) pkeys[i] = i < n ? pool[(size_t)q * cap + i] : 0ull;
+    cta_bitonic_desc(pkeys, npow2, threadIdx.x, blockDim.x, 0);
+    for (int i = threadIdx.x; i < Lc; i += blockDim.x) approx[(size_t)q * Lc + i] = pkeys[i];
+    if (threadIdx.x == 0 && ambiguous != nullptr && (cnt > cap || (cnt < Lc && g_thr[q] != 0))) atomicAdd(ambiguous, 1);
+}
+
+int dense_filter_sample_k(int Lc) {
+    int ks = (5 * Lc + 31) / 32;     // ~2.5 Lc / 16: the expected pool is 2.5 Lc rows, > 4 sigma above Lc
+    if (ks < 16) ks = 16;
+    if (ks > 64) ks = 64;
+    return ks;
+}
+
+int launch_dense_gemm_filtered(Shard* s, int batch, int Lc, uint64_t* scratch_a, uint64_t* scratch_b, uint64_t* approx,
+                               int32_t* ambiguous) {
+    const int Ks = dense_filter_sample_k(Lc);
+    int cap = next_pow2(4 * kSampleStride * Ks);
+    if (cap < 1024) cap = 1024;
+    if (cap > 8192) cap = 8192;
+    B2_TRY(s->ws.pool.ensure((size_t)batch * cap * 8 + (size_t)batch * 4, 0, s->stream));
+    uint64_t* pool = s->ws.pool.as<uint64_t>();
+    int* pool_cnt = reinterpret_cast<int*>(pool + (size_t)batch * cap);
+    s->stats.dense_path = 2;
+    s->stats.dense_passes = 0;
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[0], s->stream)); }
+    // 1. sample pass: top-Ks per query over every 16th tile (register lists, dynamic thresholds in g_thr)
+    int nl = 0;
+    B2_TRY(gemm_passes(s, batch, Ks, scratch_a, &nl, nullptr, kSampleStride, nullptr, nullptr, 0));
+    uint64_t* merged = nullptr;
+    B2_TRY(launch_merge_tree(s, batch, nl, Ks, scratch_a, scratch_b, &merged));
+    // 2. fixed threshold per query = Ks-th best of the sample
+    set_filter_thr_kernel<<<(batch + 127) / 128, 128, 0, s->stream>>>(merged, Ks, s->ws.thr.as<uint64_t>(), pool_cnt, batch);
+    B2_CUDA(cudaGetLastError());
+    // 3. filter pass over the whole shard
+    B2_TRY(gemm_passes(s, batch, Lc, nullptr, nullptr, nullptr, 1, pool, pool_cnt, cap));
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[1], s->stream)); s->ev_dense = true; }
+    // 4. best Lc of each pool
+    static bool attr = false;
+    if (!attr) {
+        B2_CUDA(cudaFuncSetAttribute(pool_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        attr = true;
+    }
+    const int npow2_max = next_pow2(cap > Lc ? cap : Lc);
+    pool_select_kernel<<<batch, 512, (size_t)npow2_max * 8, s->stream>>>(pool, pool_cnt, cap, s->ws.thr.as<uint64_t>(), Lc,
+                                                                        approx, ambiguous);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches += 2;
     s->stats.dense_bytes = (int64_t)s->stats.dense_passes * s->n_rows * s->dim * 2;
     return B200RAG_OK;
 }

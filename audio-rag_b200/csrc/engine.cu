@@ -160,11 +160,21 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             int nlists = 0;
             const bool use_gemm = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
             s->dense_stage_cap = s->dense_stage_cap_env;   // (3 x 32 KB leaves room for a co-resident sparse CTA too)
-            if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
-            else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
-            s->dense_stage_cap = 0;
             uint64_t* approx = nullptr;
-            B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
+            // tcgen05 path with a top-k too large for register lists: sample + filter (128 queries per pass whatever
+            // the top-k).  A retry (slack widened after an ambiguous result) takes the robust list path instead.
+            const bool filtered = use_gemm && Lc > 64 && s->slack == 0 && s->gemm_filter;
+            if (filtered) {
+                B2_TRY(launch_dense_gemm_filtered(s, B, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(),
+                                                  s->ws.lists_a.as<uint64_t>() + (size_t)B * nl_max * Lc - (size_t)B * Lc,
+                                                  ambiguous));
+                approx = s->ws.lists_a.as<uint64_t>() + (size_t)B * nl_max * Lc - (size_t)B * Lc;
+            } else {
+                if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
+                else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
+                B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
+            }
+            s->dense_stage_cap = 0;
             B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
             B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr,
                                        q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, out, ambiguous));
@@ -286,6 +296,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_DENSE_STAGES")) s->dense_stage_cap_env = atoi(e);
     if (const char* e = getenv("B200RAG_TILE_INTERLEAVE")) s->tile_interleave = atoi(e);
     if (const char* e = getenv("B200RAG_SCAN_SHARED")) s->scan_shared = atoi(e);
+    if (const char* e = getenv("B200RAG_GEMM_FILTER")) s->gemm_filter = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }
@@ -313,7 +324,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
     s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
-    s->ws.exact.release(); s->ws.cands.release(); s->ws.out.release();
+    s->ws.exact.release(); s->ws.pool.release(); s->ws.cands.release(); s->ws.out.release();
     s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release(); s->ws.q_eps.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (int i = 0; i < 4; ++i)

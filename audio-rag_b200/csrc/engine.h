@@ -65,6 +65,7 @@ struct Workspace {
     DevBuf lists_d;
     DevBuf exact2;
     DevBuf q_eps;         // [B] f32 absolute error bound of the sparse scan's approximate scores | [B] i32 grid-wide thresholds
+    DevBuf pool;          // filter path of the tcgen05 kernel: [B, cap] u64 keys | [B] i32 counters
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
 };
@@ -85,6 +86,7 @@ struct Shard {
     int bulk_split = 4;
     int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
     int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
+    bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
@@ -143,6 +145,10 @@ int dense_scan_nlists(const Shard* s);
 // tcgen05 + TMA GEMM with the top-k fused in the TMEM epilogue (<= 128 queries per corpus pass). Same output format.
 int launch_dense_gemm(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores);
 int dense_gemm_nlists(const Shard* s);
+// Large top-k with query batches: 1/16 sample pass -> fixed per-query thresholds -> filter pass appending to per-query
+// pools -> best Lc of each pool in approx[batch][Lc] (sorted).  Flags `ambiguous` when a pool under- or overflowed.
+int launch_dense_gemm_filtered(Shard* s, int batch, int Lc, uint64_t* scratch_a, uint64_t* scratch_b, uint64_t* approx,
+                               int32_t* ambiguous);
 
 // ---- select.cu -----------------------------------------------------------------------------------------
 // Reduce [batch, n_lists, Lc] key lists to [batch, Lc] (sorted desc) with a tree of smem bitonic merges.
