@@ -334,3 +334,35 @@ def test_large_topk_and_batches_all_paths(gpu):
     _run_and_check(sh, c, "hybrid", 150, 10, batch=150, qid_start=300)
     _run_and_check(sh, c, "sparse", 70, 20, batch=70, qid_start=500)
     sh.close()
+
+
+def test_gemm_filter_path_retry_and_robust_lists(gpu):
+    """tcgen05 path, top-100 with a query batch: (a) the sample+filter epilogue, (b) the shared-memory list epilogue it
+    replaces (forced through a fixed slack), (c) a corpus built so that the 1/16 sample over-estimates the threshold
+    (the sampled tiles hold 40 near-copies of every query, the rest of the shard none): the filter pass collects fewer
+    than Lc rows, the search must notice (ambiguous) and repeat on the robust path with the exact answer."""
+    from b200rag import normalize_bf16, synth
+    c = Corpus(20_000, dim=256, sparse=False)
+    qf, _, _, _ = c.queries(6)
+    qb = normalize_bf16(qf)
+    # rows 0..239 (tile 0, always in the sample) become the queries' nearest neighbours: 40 perturbed copies of each
+    rng = np.random.default_rng(5)
+    planted = np.repeat(qf, 40, axis=0) + 0.02 * rng.standard_normal((240, 256)).astype(np.float32)
+    c.bits[:240] = normalize_bf16(planted)
+    sh = _shard_from(c, gpu)
+    sh.set_dense_path(2)
+
+    def check(tag):
+        ids, scores, counts = sh.search("dense", 100, qb)
+        for i in range(6):
+            ei, es = oracle_search(c, "dense", qb[i], None, None, None, 100)
+            assert_result_equal(ids[i], scores[i], int(counts[i]), ei, es, ctx=f"{tag} q={i}")
+        return sh.stats()
+
+    st = check("filter+retry")
+    assert st["retries"] >= 1, "the planted sample must force the robust retry"
+    sh.set_slack(60)                      # fixed slack -> list epilogue from the start
+    st = check("robust lists")
+    assert st["retries"] == 0
+    sh.set_slack(0)
+    sh.close()
