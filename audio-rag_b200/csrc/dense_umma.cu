@@ -39,6 +39,10 @@ constexpr uint32_t kStageABytes = kGemmM * kGemmKB * 2;   // 16 KB
 constexpr uint32_t kStageBBytes = kGemmN * kGemmKB * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
 constexpr uint32_t kTmemCols = 512;
+// CTA pair (cta_group::2): M = 256 queries (128 per CTA), N = 256 corpus rows split 128 + 128 between the two CTAs
+constexpr uint32_t kStageBBytesPair = (kGemmN / 2) * kGemmKB * 2;   // 16 KB
+constexpr uint32_t kStageBytesPair = kStageABytes + kStageBBytesPair;
+constexpr int kGemmStagesPair = 6;
 
 struct GemmParams {
     const void* corpus;            // for the contiguous L2 prefetch
@@ -91,6 +95,50 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants.  The pair's leader is the CTA whose shared-window address has the peer bit
+// (bit 24) clear; masking an mbarrier address with kPeerMask names the LEADER's copy of that barrier from either CTA.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the pair's MMAs so far have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -144,6 +192,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = 256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
                             ((uint32_t)(kGemmM >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
+                                ((uint32_t)((2 * kGemmM) >> 4) << 24);   // M = 256 across the pair
 
 // LREG > 0: each epilogue lane keeps its query's candidate list SORTED IN REGISTERS (LREG keys; Lc <= LREG; the
 //           threshold is the LREG-th best, slightly weaker than the Lc-th, which only admits a few more inserts).
@@ -153,18 +203,26 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGe
 //            the shard, see launch_dense_gemm_filtered); every score at or above it is appended to the query's pool in
 //            global memory (~16 K_s keys per query over the whole shard).  The epilogue carries no per-query state
 //            besides one register, so 128 queries per pass fit whatever the top-k (smem lists: 32 at top-100).
-template <int LREG>
+// CG == 2: the kernel runs as CTA PAIRS (cluster of 2, cta_group::2): one tcgen05.mma covers 256 queries x 256 rows,
+//          each CTA stages its own 128 queries and HALF of the corpus tile, so a corpus row crosses L2 -> SM once
+//          per 256 queries instead of once per 128 and a whole batch of 256 needs ONE pass over HBM.  The leader CTA
+//          issues the MMAs; commits are multicast to both CTAs' barriers; each CTA's epilogue reads its own TMEM.
+template <int LREG, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                   const GemmParams p) {
+    constexpr uint32_t STAGE_BYTES = CG == 2 ? kStageBytesPair : kStageBytes;
+    constexpr int MAX_STAGES = CG == 2 ? kGemmStagesPair : kGemmStages;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     extern __shared__ uint8_t gsm_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles
     // (offset arithmetic on the shared window keeps the pointer in the shared address space: LDS/STS, not generic)
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
     const int S = p.stages;
-    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);
-    uint64_t* empty = full + kGemmStages;
-    uint64_t* tfull = empty + kGemmStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + (size_t)S * STAGE_BYTES);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 2);   // (16 u64 barrier slots precede: 16-byte aligned)
     float* stage_s = reinterpret_cast<float*>(tmem_base_s + 4);          // [4 epilogue warps][32 lanes][33] score staging
@@ -172,19 +230,24 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.dim / kGemmKB;
-    const int64_t t0 = p.n_tiles * (int64_t)blockIdx.x / (int64_t)gridDim.x;
-    const int64_t t1 = p.n_tiles * (int64_t)(blockIdx.x + 1) / (int64_t)gridDim.x;
+    const int64_t unit = (int64_t)blockIdx.x / CG, units = (int64_t)gridDim.x / CG;   // CTA (or CTA pair) and their number
+    const int64_t t0 = p.n_tiles * unit / units;
+    const int64_t t1 = p.n_tiles * (unit + 1) / units;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_q);
         prefetch_tmap(&map_c);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * CG); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_base_s, kTmemCols);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_pair(tmem_base_s, kTmemCols);
+        else tmem_alloc(tmem_base_s, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
 
@@ -196,17 +259,25 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             for (int64_t t = t0; t < t1; ++t) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1u);
-                    uint8_t* sa = gsm + (size_t)st * kStageBytes;
-                    mbar_arrive_expect_tx(&full[st], kStageBytes);
-                    tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
-                    tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * p.tile_stride * kGemmN));
+                    uint8_t* sa = gsm + (size_t)st * STAGE_BYTES;
+                    if (CG == 2) {
+                        // both CTAs' copies complete on the LEADER's full barrier (which expects the pair's bytes)
+                        if (leader) mbar_arrive_expect_tx(&full[st], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(sa, &map_q, &full[st], kb * kGemmKB, (int)rank * kGemmM);
+                        tma_load_2d_pair(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB,
+                                         (int)(t * p.tile_stride * kGemmN) + (int)rank * (kGemmN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
+                        tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * p.tile_stride * kGemmN));
+                    }
                     if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             int st = 0;
             uint32_t ph = 0;
             int it = 0;
@@ -218,15 +289,19 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(gsm + (size_t)st * kStageBytes);
+                    const uint32_t sa = smem_u32(gsm + (size_t)st * STAGE_BYTES);
                     const uint64_t da = make_sw128_desc(sa);
                     const uint64_t db = make_sw128_desc(sa + kStageABytes);
 #pragma unroll
-                    for (int k = 0; k < kGemmKB / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc,
-                                  (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty[st]);             // frees the smem stage when these MMAs retire
-                    if (kb == nkb - 1) umma_commit(&tfull[buf]);
+                    for (int k = 0; k < kGemmKB / 16; ++k) {
+                        if (CG == 2) umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdescPair,
+                                                    (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if (CG == 2) umma_commit_pair(&empty[st]); else umma_commit(&empty[st]);
+                    if (kb == nkb - 1) { if (CG == 2) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]); }
                     if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
@@ -234,9 +309,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else if (warp >= 4) {
         // ------------------------------------------------------------------------------------ epilogue
         const int quad = warp - 4;                       // == warp % 4: the TMEM lane quadrant this warp may read
-        const int qi = quad * 32 + lane;                 // my query
+        const int qi = (int)rank * kGemmM + quad * 32 + lane;   // my query
         const bool active = qi < p.batch;
-        const bool warp_active = quad * 32 < p.batch;
+        const bool warp_active = (int)rank * kGemmM + quad * 32 < p.batch;
         const int Lp = (p.Lc + 1) & ~1;
         uint64_t* wlists = lists_s + (size_t)(quad * 32) * Lp;     // this warp's 32 lists (LREG == 0 only)
         const uint32_t* mask = (active && p.masks != nullptr) ? p.masks[qi] : nullptr;
@@ -333,13 +408,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
         }
         __syncwarp();
         if constexpr (LREG > 0) {
             // my list is already sorted: first Lc keys -> global [q][cta][Lc]
             if (active) {
-                uint64_t* o = p.out + (size_t)qi * p.out_q_stride + (size_t)blockIdx.x * p.Lc;
+                uint64_t* o = p.out + (size_t)qi * p.out_q_stride + (size_t)unit * p.Lc;   // one list per CTA (pair)
 #pragma unroll
                 for (int i = 0; i < LREG; ++i)
                     if (i < p.Lc) o[i] = L[i];
@@ -358,10 +433,12 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     // ---- teardown: everyone meets, then the allocating warp frees TMEM
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer may still be reading operands / signalling this CTA's barriers
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -398,50 +475,73 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, i
 
 int dense_gemm_nlists(const Shard* s) { return s->sm_count; }
 
-template <int LREG>
+template <int LREG, int CG>
 static int launch_gemm_t(Shard* s, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmParams& p, int grid,
                          size_t smem) {
-    auto kern = dense_gemm_kernel<LREG>;
+    auto kern = dense_gemm_kernel<LREG, CG>;
     static bool attr = false;
     if (!attr) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    kern<<<grid, kGemmThreads, smem, s->stream>>>(map_q, map_c, p);
-    B2_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, kern, map_q, map_c, p));
     return B200RAG_OK;
 }
 
-// One or more corpus passes of <= 128 queries each.  tile_stride > 1 scores only every tile_stride-th 256-row tile (the
-// sample pass); pool != nullptr selects the filter epilogue (no lists: out_lists unused).
+// One or more corpus passes.  A pass takes up to 256 queries on CTA pairs (cta_group::2) when more than 128 remain
+// and the epilogue keeps no shared-memory lists, else up to 128 on single CTAs.  tile_stride > 1 scores only every
+// tile_stride-th 256-row tile (the sample pass); pool != nullptr selects the filter epilogue (out_lists unused).
+// List layout: out_lists[q][nl][Lc] with nl = *nlists for EVERY query (passes on pairs fill only nl/2... see below).
 static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists, float* dbg_scores, int tile_stride,
                        uint64_t* pool, int* pool_cnt, int pool_cap) {
     const int64_t all_tiles = (s->n_rows + kGemmN - 1) / kGemmN;
     const int64_t n_tiles = (all_tiles + tile_stride - 1) / tile_stride;
-    int grid = s->sm_count;
-    if (n_tiles < grid) grid = (int)(n_tiles > 0 ? n_tiles : 1);
-    if (nlists != nullptr) *nlists = grid;
+    int grid1 = s->sm_count;                       // single-CTA passes
+    if (n_tiles < grid1) grid1 = (int)(n_tiles > 0 ? n_tiles : 1);
+    int units2 = s->sm_count / 2;                  // CTA-pair passes
+    if (n_tiles < units2) units2 = (int)(n_tiles > 0 ? n_tiles : 1);
+    if (nlists != nullptr) *nlists = grid1;        // slots per query; a pair pass writes units2 <= grid1 of them, zeros the rest
     const bool filter = pool != nullptr;
     const int lreg = filter ? -1 : (Lc <= 32 ? 32 : (Lc <= 64 ? 64 : 0));
-    // shared memory: S pipeline stages (48 KB each) + score staging (+ one list of Lc keys per query when the lists
-    // do not fit in registers)
+    const bool pairs_ok = s->gemm_pairs && lreg != 0 && dbg_scores == nullptr;
+    // shared memory: S pipeline stages + score staging (+ one list of Lc keys per query when the lists do not fit
+    // in registers)
     const size_t max_smem = 227 * 1024, fixed = 1024 + 512 + 4 * 32 * 33 * 4;
     const int Lp = (Lc + 1) & ~1;
     const size_t per_q = lreg != 0 ? 0 : (size_t)Lp * 8;
-    int qpp = kGemmM;                                   // queries per pass
+    int qpp = kGemmM;                                   // queries per single-CTA pass
     while (qpp > 32 && fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) qpp -= 32;
     if (fixed + 2 * (size_t)kStageBytes + (size_t)qpp * per_q > max_smem) {
         set_error("dense_gemm: top-k too large for shared memory");
         return B200RAG_ERR_INVALID;
     }
-    CUtensorMap map_c;
+    CUtensorMap map_c, map_c2;
     B2_TRY(make_map(&map_c, s->dense.p, s->n_rows, s->dim, kGemmN));
-    for (int q0 = 0; q0 < batch; q0 += qpp) {
-        const int nq = batch - q0 < qpp ? batch - q0 : qpp;
-        const size_t list_bytes = (size_t)((nq + 31) / 32 * 32) * per_q;
-        int stages = (int)((max_smem - fixed - list_bytes) / kStageBytes);
-        if (stages > kGemmStages) stages = kGemmStages;
-        const size_t smem = fixed + (size_t)stages * kStageBytes + list_bytes;
+    if (pairs_ok) B2_TRY(make_map(&map_c2, s->dense.p, s->n_rows, s->dim, kGemmN / 2));
+    int q0 = 0;
+    while (q0 < batch) {
+        const bool pair = pairs_ok && batch - q0 > kGemmM;
+        const int cap_q = pair ? 2 * kGemmM : qpp;
+        const int nq = batch - q0 < cap_q ? batch - q0 : cap_q;
+        const size_t list_bytes = pair ? 0 : (size_t)((nq + 31) / 32 * 32) * per_q;
+        const size_t stage_bytes = pair ? kStageBytesPair : kStageBytes;
+        int stages = (int)((max_smem - fixed - list_bytes) / stage_bytes);
+        const int max_stages = pair ? kGemmStagesPair : kGemmStages;
+        if (stages > max_stages) stages = max_stages;
+        const size_t smem = fixed + (size_t)stages * stage_bytes + list_bytes;
+        const int grid = pair ? 2 * units2 : grid1;
         CUtensorMap map_q;
         B2_TRY(make_map(&map_q, s->ws.q_bits.as<uint16_t>() + (size_t)q0 * s->dim, nq, s->dim, kGemmM));
         GemmParams p{};
@@ -452,8 +552,8 @@ static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nl
         p.batch = nq;
         p.masks = s->h_masks.empty() ? nullptr : s->ws.q_masks.as<const uint32_t*>() + q0;
         p.g_thr = s->ws.thr.as<uint64_t>() + q0;
-        p.out = filter ? nullptr : out_lists + (size_t)q0 * grid * Lc;
-        p.out_q_stride = (int64_t)grid * Lc;
+        p.out = filter ? nullptr : out_lists + (size_t)q0 * grid1 * Lc;
+        p.out_q_stride = (int64_t)grid1 * Lc;
         p.Lc = Lc;
         p.stages = stages;
         p.tile_stride = tile_stride;
@@ -461,12 +561,23 @@ static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nl
         p.pool_cnt = filter ? pool_cnt + q0 : nullptr;
         p.pool_cap = pool_cap;
         p.dbg_scores = dbg_scores != nullptr ? dbg_scores + (size_t)q0 * s->n_rows : nullptr;
-        if (lreg < 0) B2_TRY(launch_gemm_t<-1>(s, map_q, map_c, p, grid, smem));
-        else if (lreg == 32) B2_TRY(launch_gemm_t<32>(s, map_q, map_c, p, grid, smem));
-        else if (lreg == 64) B2_TRY(launch_gemm_t<64>(s, map_q, map_c, p, grid, smem));
-        else B2_TRY(launch_gemm_t<0>(s, map_q, map_c, p, grid, smem));
+        if (pair && !filter && units2 < grid1) {
+            // a pair pass fills list slots [0, units2) of each of its queries: the others must read as "no candidate"
+            B2_CUDA(cudaMemsetAsync(p.out, 0, (size_t)nq * grid1 * Lc * 8, s->stream));
+        }
+        if (pair) {
+            if (lreg < 0) B2_TRY((launch_gemm_t<-1, 2>(s, map_q, map_c2, p, grid, smem)));
+            else if (lreg == 32) B2_TRY((launch_gemm_t<32, 2>(s, map_q, map_c2, p, grid, smem)));
+            else B2_TRY((launch_gemm_t<64, 2>(s, map_q, map_c2, p, grid, smem)));
+        } else {
+            if (lreg < 0) B2_TRY((launch_gemm_t<-1, 1>(s, map_q, map_c, p, grid, smem)));
+            else if (lreg == 32) B2_TRY((launch_gemm_t<32, 1>(s, map_q, map_c, p, grid, smem)));
+            else if (lreg == 64) B2_TRY((launch_gemm_t<64, 1>(s, map_q, map_c, p, grid, smem)));
+            else B2_TRY((launch_gemm_t<0, 1>(s, map_q, map_c, p, grid, smem)));
+        }
         s->stats.kernel_launches++;
         if (tile_stride == 1) s->stats.dense_passes++;
+        q0 += nq;
     }
     return B200RAG_OK;
 }

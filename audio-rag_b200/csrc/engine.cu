@@ -297,6 +297,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_TILE_INTERLEAVE")) s->tile_interleave = atoi(e);
     if (const char* e = getenv("B200RAG_SCAN_SHARED")) s->scan_shared = atoi(e);
     if (const char* e = getenv("B200RAG_GEMM_FILTER")) s->gemm_filter = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_GEMM_PAIRS")) s->gemm_pairs = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }

@@ -86,6 +86,7 @@ struct Shard {
     int bulk_split = 4;
     int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
     int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
+    bool gemm_pairs = true;               // knob: CTA pairs (cta_group::2, 256 queries per corpus pass) when > 128 queries remain
     bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
