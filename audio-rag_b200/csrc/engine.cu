@@ -172,12 +172,19 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             } else {
                 if (use_gemm) B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, nullptr));
                 else B2_TRY(launch_dense_scan(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists));
-                B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
+                if (!(s->fused_tail && leg_tail_fits(nlists, Lc)))
+                    B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
             }
             s->dense_stage_cap = 0;
-            B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
-            B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr,
-                                       q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, out, ambiguous));
+            const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
+            if (approx == nullptr) {
+                B2_TRY(launch_leg_tail(s, false, B, nlists, Lc, L, s->ws.lists_a.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
+                                       q.score_threshold, out, ambiguous));
+            } else {
+                B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
+                B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
+                                           q.score_threshold, out, ambiguous));
+            }
         }
     }
     if (want_sparse) {
@@ -195,10 +202,15 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_CUDA(cudaMemsetAsync(s->ws.q_eps.as<int32_t>() + B, 0x80, (size_t)B * 4, sst));   // thresholds: 0x80808080 < any score
             s->stream = sst;                                   // the launchers below enqueue on s->stream
             int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.q_eps.as<float>(), s->ws.q_eps.as<int>() + B);
-            uint64_t* approx = nullptr;
-            if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, sp_lists, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
-            if (rc == B200RAG_OK) rc = launch_rescore_sparse(s, B, Lc, approx, s->ws.exact2.as<uint64_t>());
-            if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
+            if (s->fused_tail && leg_tail_fits(sp_lists, Lc)) {
+                if (rc == B200RAG_OK) rc = launch_leg_tail(s, true, B, sp_lists, Lc, L, s->ws.lists_c.as<uint64_t>(), 1e-12f, 2e-6f,
+                                                           s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
+            } else {
+                uint64_t* approx = nullptr;
+                if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, sp_lists, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
+                if (rc == B200RAG_OK) rc = launch_rescore_sparse(s, B, Lc, approx, s->ws.exact2.as<uint64_t>());
+                if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
+            }
             s->stream = st;
             if (rc != B200RAG_OK) return rc;
         }
@@ -298,6 +310,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_SCAN_SHARED")) s->scan_shared = atoi(e);
     if (const char* e = getenv("B200RAG_GEMM_FILTER")) s->gemm_filter = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_GEMM_PAIRS")) s->gemm_pairs = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_FUSED_TAIL")) s->fused_tail = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }

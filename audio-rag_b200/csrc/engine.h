@@ -86,6 +86,7 @@ struct Shard {
     int bulk_split = 4;
     int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
     int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
+    bool fused_tail = true;               // knob: merge + re-score + finalize of a leg in one launch when the lists fit shared memory
     bool gemm_pairs = true;               // knob: CTA pairs (cta_group::2, 256 queries per corpus pass) when > 128 queries remain
     bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
@@ -161,6 +162,10 @@ int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, u
 int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
                         float eps_abs, float eps_rel, const float* eps_abs_q /*[batch] or null*/, int has_thr, float thr,
                         b200rag_cand* out, int32_t* ambiguous);
+// merge (all levels) + exact re-score + finalize in one launch, when n_lists * Lc keys fit (leg_tail_fits)
+bool leg_tail_fits(int n_lists, int Lc);
+int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L, const uint64_t* lists, float eps_abs,
+                    float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
                 int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts);
 

@@ -236,6 +236,261 @@ int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* appr
     return B200RAG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ fused leg tail
+// merge_lists (all levels) + rescore + finalize_leg in ONE launch per leg, for list sets that fit shared memory
+// (n_lists * Lc <= kTailMaxKeys).  After the scan every further launch is pure latency (4-5 launches of 5-15 us each
+// plus the gaps between them), which is what caps strong scaling on small shards.
+//   1. every thread takes a strided slice of the n_lists * Lc keys and keeps its maximum; each warp sorts its 32 maxima
+//      in registers and publishes its k-th largest, k = ceil(Lc / #warps); the minimum over the warps has >= Lc keys at
+//      or above it, so only those survivors (typically a few Lc) are compacted and bitonic-sorted
+//   2. the best Lc are re-scored exactly, one warp per candidate (same canonical order as the standalone kernels)
+//   3. exact keys are sorted, thresholded, guarded and emitted exactly like finalize_leg_kernel
+constexpr int kTailMaxKeys = 8192;
+constexpr int kTailSurvivorCap = 2048;
+
+__device__ __forceinline__ uint64_t rescore_dense_warp(const uint16_t* __restrict__ corpus, int dim,
+                                                       const uint16_t* __restrict__ q_bits, int q, uint32_t row, int lane) {
+    const uint4* rp = reinterpret_cast<const uint4*>(corpus + (size_t)row * dim);
+    const uint4* qp = reinterpret_cast<const uint4*>(q_bits + (size_t)q * dim);
+    const int nch = dim / 256;
+    uint4 cv[4], qv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < nch) { cv[c] = rp[c * 32 + lane]; qv[c] = qp[c * 32 + lane]; }
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < nch) {
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].x), bf16lo_d(qv[c].x)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].x), bf16hi_d(qv[c].x)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].y), bf16lo_d(qv[c].y)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].y), bf16hi_d(qv[c].y)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].z), bf16lo_d(qv[c].z)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].z), bf16hi_d(qv[c].z)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16lo_d(cv[c].w), bf16lo_d(qv[c].w)));
+            acc = __dadd_rn(acc, __dmul_rn(bf16hi_d(cv[c].w), bf16hi_d(qv[c].w)));
+        }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+    return make_key(__double2float_rn(acc) + 0.0f, row);
+}
+
+struct TailParams {
+    const uint64_t* lists;   // [batch][n_lists][Lc]
+    int n_lists, Lc, L;
+    // dense re-score
+    const uint16_t* corpus;
+    int dim;
+    const uint16_t* q_bits;
+    // sparse re-score
+    const int64_t* fwd_ptr;
+    const uint32_t* fwd_terms;
+    const float* fwd_w;
+    const int64_t* q_indptr;
+    const uint32_t* q_terms;
+    const float* q_w;
+    // finalize
+    float eps_abs, eps_rel;
+    const float* eps_abs_q;
+    int has_thr;
+    float thr;
+    int64_t row_base;
+    b200rag_cand* out;       // [batch][L]
+    int32_t* ambiguous;
+};
+
+template <bool SPARSE, int NT>
+__global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
+    extern __shared__ __align__(16) uint64_t tkeys[];     // [kTailSurvivorCap] survivors, later [npow2(Lc)] exact keys
+    constexpr int NW = NT / 32;
+    __shared__ uint64_t wk_s[NW];
+    __shared__ int cnt_s, nvalid_s;
+    __shared__ uint64_t last_s;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = p.n_lists * p.Lc;
+    const uint64_t* src = p.lists + (size_t)q * total;
+    if (tid == 0) { cnt_s = 0; nvalid_s = 0; }
+
+    // ---- 1. threshold from thread maxima, survivors, sort
+    uint64_t tmax = 0;
+    for (int i = tid; i < total; i += NT) {
+        const uint64_t k = src[i];
+        tmax = k > tmax ? k : tmax;
+    }
+    {
+        uint64_t v = tmax;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool keep_max = (((lane & j) == 0) == ((lane & k) == 0));
+                v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+            }
+        const int kk = (p.Lc + NW - 1) / NW;
+        const uint64_t kth = kk <= 32 ? __shfl_sync(0xffffffffu, v, kk - 1) : 0ull;
+        if (lane == 0) wk_s[warp] = kth;
+    }
+    __syncthreads();
+    uint64_t tau = wk_s[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) tau = wk_s[w] < tau ? wk_s[w] : tau;
+    if (tau == 0) tau = 1;                 // fewer than Lc real keys: keep every non-empty slot
+    for (int i = tid; i < total; i += NT) {
+        const uint64_t k = src[i];
+        if (k >= tau) {
+            const int pos = atomicAdd(&cnt_s, 1);
+            if (pos < kTailSurvivorCap) tkeys[pos] = k;
+        }
+    }
+    __syncthreads();
+    int M = cnt_s;
+    if (M > kTailSurvivorCap) {
+        // (massive ties) exact Lc-th largest key by bisection on the key bits, then exactly the keys >= it
+        __shared__ int c_s;
+        uint64_t K = 0;
+        for (int bit = 63; bit >= 0; --bit) {
+            const uint64_t cand = K | (1ull << bit);
+            int c = 0;
+            for (int i = tid; i < total; i += NT) c += src[i] >= cand ? 1 : 0;
+            if (tid == 0) c_s = 0;
+            __syncthreads();
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0 && c) atomicAdd(&c_s, c);
+            __syncthreads();
+            if (c_s >= p.Lc) K = cand;
+            __syncthreads();
+        }
+        if (tid == 0) cnt_s = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += NT) {
+            const uint64_t k = src[i];
+            if (k >= K && k != 0) {
+                const int pos = atomicAdd(&cnt_s, 1);
+                if (pos < kTailSurvivorCap) tkeys[pos] = k;
+            }
+        }
+        __syncthreads();
+        M = cnt_s < kTailSurvivorCap ? cnt_s : kTailSurvivorCap;
+    }
+    int npow2 = next_pow2(M > p.Lc ? M : p.Lc);
+    for (int i = M + tid; i < npow2; i += NT) tkeys[i] = 0;
+    cta_bitonic_desc(tkeys, npow2, tid, NT, 0);
+    if (tid == 0) last_s = tkeys[p.Lc - 1];      // weakest retained approximate key (0: nothing was cut)
+    __syncthreads();
+
+    // ---- 2. exact re-score of the best Lc, in place
+    if constexpr (!SPARSE) {
+        for (int i = warp; i < p.Lc; i += NW) {
+            const uint64_t key = tkeys[i];
+            uint64_t ex = 0;
+            if (key != 0) ex = rescore_dense_warp(p.corpus, p.dim, p.q_bits, q, key_row(key), lane);
+            __syncwarp();
+            if (lane == 0) tkeys[i] = ex;
+        }
+    } else {
+        __shared__ uint32_t qt[kMaxQueryTermsChunk];
+        __shared__ float qw[kMaxQueryTermsChunk];
+        __shared__ double prod[NW][kMaxQueryTermsChunk];
+        __shared__ uint8_t present[NW][kMaxQueryTermsChunk];
+        const int64_t qs = p.q_indptr[q], qe = p.q_indptr[q + 1];
+        for (int i0 = 0; i0 < p.Lc; i0 += NW) {
+            const int i = i0 + warp;
+            const uint64_t key = i < p.Lc ? tkeys[i] : 0ull;
+            const bool active = key != 0;
+            const uint32_t row = key_row(key);
+            int64_t ds = 0, de = 0;
+            if (active) { ds = p.fwd_ptr[row]; de = p.fwd_ptr[row + 1]; }
+            double acc = 0.0;
+            for (int64_t c0 = qs; c0 < qe; c0 += kMaxQueryTermsChunk) {
+                const int cn = (int)min((int64_t)kMaxQueryTermsChunk, qe - c0);
+                __syncthreads();
+                for (int j = tid; j < cn; j += NT) { qt[j] = p.q_terms[c0 + j]; qw[j] = p.q_w[c0 + j]; }
+                __syncthreads();
+                if (active) {
+                    for (int j = lane; j < cn; j += 32) {
+                        const uint32_t t = qt[j];
+                        int64_t lo = ds, hi = de;
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (p.fwd_terms[mid] < t) lo = mid + 1; else hi = mid;
+                        }
+                        const bool hit = lo < de && p.fwd_terms[lo] == t;
+                        present[warp][j] = hit ? 1 : 0;
+                        if (hit) prod[warp][j] = __dmul_rn((double)qw[j], (double)p.fwd_w[lo]);
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int j = 0; j < cn; ++j)
+                            if (present[warp][j]) acc = __dadd_rn(acc, prod[warp][j]);
+                    __syncwarp();
+                }
+            }
+            if (i < p.Lc && lane == 0) tkeys[i] = active ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. finalize: threshold, order, guard, emit
+    const int fpow2 = next_pow2(p.Lc);
+    for (int i = tid; i < fpow2; i += NT) {
+        uint64_t k = i < p.Lc ? tkeys[i] : 0ull;
+        if (k != 0 && p.has_thr && key_score(k) < p.thr) k = 0;
+        tkeys[i] = k;
+    }
+    cta_bitonic_desc(tkeys, fpow2, tid, NT, 0);
+    int local = 0;
+    for (int i = tid; i < fpow2; i += NT) local += tkeys[i] != 0 ? 1 : 0;
+    if (local) atomicAdd(&nvalid_s, local);
+    __syncthreads();
+    const int nvalid = nvalid_s;
+    for (int i = tid; i < p.L; i += NT) {
+        const uint64_t k = tkeys[i];
+        b200rag_cand c;
+        c.id = k != 0 ? p.row_base + (int64_t)key_row(k) : -1;
+        c.score = k != 0 ? key_score(k) : 0.f;
+        c.valid = k != 0 ? 1u : 0u;
+        p.out[(size_t)q * p.L + i] = c;
+    }
+    if (tid == 0 && p.ambiguous != nullptr) {
+        const uint64_t last = last_s;
+        if (last != 0) {  // the approximate list was full: rows outside it exist, bounded by `a`
+            const float a = key_score(last);
+            bool have_bound = false;
+            float bound = 0.f;
+            if (nvalid >= p.L) { bound = key_score(tkeys[p.L - 1]); have_bound = true; }
+            else if (p.has_thr) { bound = p.thr; have_bound = true; }
+            if (!have_bound) {
+                atomicAdd(p.ambiguous, 1);
+            } else {
+                const float eps = p.eps_abs + (p.eps_abs_q != nullptr ? p.eps_abs_q[q] : 0.f) +
+                                  p.eps_rel * fmaxf(fabsf(a), fabsf(bound));
+                if (a + eps >= bound) atomicAdd(p.ambiguous, 1);
+            }
+        }
+    }
+}
+
+bool leg_tail_fits(int n_lists, int Lc) { return (int64_t)n_lists * Lc <= kTailMaxKeys; }
+
+int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L, const uint64_t* lists, float eps_abs,
+                    float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out,
+                    int32_t* ambiguous) {
+    TailParams p{};
+    p.lists = lists; p.n_lists = n_lists; p.Lc = Lc; p.L = L;
+    p.corpus = s->dense.as<uint16_t>(); p.dim = s->dim; p.q_bits = s->ws.q_bits.as<uint16_t>();
+    p.fwd_ptr = s->fwd_ptr.as<int64_t>(); p.fwd_terms = s->fwd_terms.as<uint32_t>(); p.fwd_w = s->fwd_w.as<float>();
+    p.q_indptr = s->ws.q_sp_indptr.as<int64_t>(); p.q_terms = s->ws.q_sp_terms.as<uint32_t>(); p.q_w = s->ws.q_sp_w.as<float>();
+    p.eps_abs = eps_abs; p.eps_rel = eps_rel; p.eps_abs_q = eps_abs_q; p.has_thr = has_thr; p.thr = thr;
+    p.row_base = s->cfg.row_base; p.out = out; p.ambiguous = ambiguous;
+    const size_t smem = (size_t)kTailSurvivorCap * 8;
+    if (sparse) leg_tail_kernel<true, 256><<<batch, 256, smem, s->stream>>>(p);
+    else leg_tail_kernel<false, 512><<<batch, 512, smem, s->stream>>>(p);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ fuse
 __device__ __forceinline__ bool cand_better(const b200rag_cand& f, const b200rag_cand& e) {
     const uint32_t fo = ord_f32(f.score), eo = ord_f32(e.score);
