@@ -82,6 +82,11 @@ SYMBOLS = [
     ("b200rag_legs_len", C.c_int, [C.POINTER(Query), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b200rag_legs", C.c_int, [_P, _P, _P]),
     ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    ("b200rag_p2p_export", C.c_int, [_P, C.c_int32, C.c_int64, _P]),
+    ("b200rag_p2p_attach", C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    ("b200rag_p2p_exchange", C.c_int, [_P, _P, C.c_int64]),
+    ("b200rag_p2p_fuse", C.c_int, [_P, _P, _P, _P]),
+    ("b200rag_p2p_close", C.c_int, [_P]),
     ("b200rag_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200rag_set_profiling", C.c_int, [_P, C.c_int32]),
     ("b200rag_synth_dense", C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P]),
@@ -289,6 +294,28 @@ class Shard:
     def fuse(self, gathered_dev, n_shards, out_ids_dev, out_scores_dev, out_counts_dev, has_trailer=False):
         check(self._lib.b200rag_fuse(self._h, _ptr(gathered_dev), n_shards, 1 if has_trailer else 0, _ptr(out_ids_dev),
                                      _ptr(out_scores_dev), _ptr(out_counts_dev)))
+
+    # ---- peer-memory candidate exchange (replaces the all-gather between legs and fuse on one box)
+    IPC_HANDLE_BYTES = 64
+
+    def p2p_export(self, world: int, slot_bytes: int) -> bytes:
+        h = (C.c_uint8 * self.IPC_HANDLE_BYTES)()
+        check(self._lib.b200rag_p2p_export(self._h, world, slot_bytes, C.cast(h, _P)))
+        return bytes(h)
+
+    def p2p_attach(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == world * self.IPC_HANDLE_BYTES
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        check(self._lib.b200rag_p2p_attach(self._h, rank, world, C.cast(buf, _P)))
+
+    def p2p_exchange(self, mine_dev, nbytes: int):
+        check(self._lib.b200rag_p2p_exchange(self._h, _ptr(mine_dev), nbytes))
+
+    def p2p_fuse(self, out_ids_dev, out_scores_dev, out_counts_dev):
+        check(self._lib.b200rag_p2p_fuse(self._h, _ptr(out_ids_dev), _ptr(out_scores_dev), _ptr(out_counts_dev)))
+
+    def p2p_close(self):
+        check(self._lib.b200rag_p2p_close(self._h))
 
     def set_profiling(self, on: bool):
         check(self._lib.b200rag_set_profiling(self._h, 1 if on else 0))

@@ -8,9 +8,16 @@ under R5): [nlegs, B, L] 16-byte candidates + one trailer per rank, <= 1.6 MB pe
 fused result is identical on all ranks and bit-identical to a single-shard search (RRF needs GLOBAL ranks, so it
 runs after the gather, never per shard).
 
+On one box the exchange does not go through a collective at all: every rank exports an exchange window over CUDA
+IPC, `b200rag_p2p_exchange` stores the rank's block into all peers' windows with NVLink peer stores and publishes an
+epoch flag, and the fuse kernel itself waits for the flags (include/b200rag.h, "peer-memory candidate exchange").
+The NCCL all-gather stays as the fallback (B200RAG_P2P=0, blocks larger than the window slot, non-CUDA test doubles).
+
 torch is plumbing only: it owns the exchange buffers and the process group; all compute is `libb200rag.so`.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -38,6 +45,36 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs: dict = {}
+        self.p2p = False
+        self.p2p_slot_bytes = int(os.environ.get("B200RAG_P2P_SLOT_BYTES", 8 << 20))
+        if self.world > 1 and device.type == "cuda" and hasattr(shard, "p2p_export") and \
+                os.environ.get("B200RAG_P2P", "1") != "0":
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Exchange CUDA IPC handles of the per-rank windows; every rank must succeed or all fall back to NCCL."""
+        ok, handle = 1, b""
+        try:
+            handle = self.shard.p2p_export(self.world, self.p2p_slot_bytes)
+        except Exception:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, handle), group=self.group)
+        if all(h[0] for h in handles):
+            try:
+                self.shard.p2p_attach(self.rank, self.world, b"".join(h[1] for h in handles))
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ok, group=self.group)
+        self.p2p = all(oks)
+        if not self.p2p and ok:
+            try:
+                self.shard.p2p_close()
+            except Exception:
+                pass
 
     def _buffers(self, nlegs, B, L, k):
         key = (nlegs, B, L, k)
@@ -78,8 +115,12 @@ class ShardedSearcher:
         nlegs, B, L, k = self._cur
         b = self._buffers(nlegs, B, L, k)
         mine, allb, out = b["mine"], b["all"], b["out"]
-        mine[-1].zero_()
-        self.shard.legs(mine, mine[-1])
+        self.shard.legs(mine, mine[-1])                    # (legs zeroes the trailer's ambiguity counter itself)
+        if self.world > 1 and self.p2p and mine.numel() * 8 <= self.p2p_slot_bytes:
+            # peer stores into every rank's window + epoch flags; the fuse kernel waits for the flags itself
+            self.shard.p2p_exchange(mine, mine.numel() * 8)
+            self.shard.p2p_fuse(out[:B * k], out[B * k:2 * B * k], out[2 * B * k:])
+            return b
         if self.world > 1:
             # output as the concatenation along dim 0 (the layout both NCCL and gloo accept)
             dist.all_gather_into_tensor(allb.view(-1, 2), mine, group=self.group)
@@ -109,6 +150,8 @@ class ShardedSearcher:
         slack0 = None
         for attempt in range(max_retries + 1):
             ids, scores, counts, amb = self.fetch(self.run_staged())
+            if amb < 0:
+                raise RuntimeError("sharded search: a peer's candidates never arrived (exchange flag timed out)")
             if amb == 0 or attempt == max_retries:
                 break
             # some shard's slack guard failed: widen on every rank (same decision everywhere: amb is global)

@@ -227,6 +227,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
 
 using namespace b200rag;
 
+static void p2p_release(Shard* s);
+
 extern "C" {
 
 const char* b200rag_version(void) { return "b200rag 0.1 (sm_100a)"; }
@@ -334,6 +336,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     if (s == nullptr) return;
     cudaSetDevice(s->cfg.device);
     cudaStreamSynchronize(s->stream);
+    p2p_release(s);
     s->dense.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
@@ -598,6 +601,7 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     B2_TRY(use_device(s));
     s->stats = b200rag_stats{};
     s->ev_dense = s->ev_sparse = false;
+    if (ambiguous_dev != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));   // callers need not pre-zero it
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
 
@@ -668,6 +672,108 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
     memcpy(out_counts, hres + o_cnt, (size_t)B * 4);
     s->stats.kernel_launches = launches;
     s->stats.retries = retries;
+    return B200RAG_OK;
+}
+
+}  // extern "C"
+
+// ---- peer-memory exchange --------------------------------------------------------------------------------------
+static void p2p_release(Shard* s) {
+    for (int r = 0; r < (int)s->xpeers.size(); ++r)
+        if (r != s->x_rank && s->xpeers[(size_t)r] != nullptr) cudaIpcCloseMemHandle(s->xpeers[(size_t)r]);
+    s->xpeers.clear();
+    if (s->xwin != nullptr) cudaFree(s->xwin);
+    s->xwin = nullptr;
+    s->ws.xpeers_dev.release();
+    s->x_world = 0;
+    cudaGetLastError();
+}
+
+static size_t p2p_window_bytes(int world, int64_t slot_bytes) {
+    return (size_t)2 * world * slot_bytes + (size_t)world * kFlagStrideU64 * 8;
+}
+
+extern "C" {
+
+int b200rag_p2p_export(b200rag_shard* sp, int32_t world, int64_t slot_bytes, uint8_t* handle_out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || handle_out == nullptr || world < 1 || world > 64 || slot_bytes < 16 || slot_bytes % 16 != 0) {
+        set_error("p2p_export: bad argument");
+        return B200RAG_ERR_INVALID;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200RAG_IPC_HANDLE_BYTES, "IPC handle size");
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    p2p_release(s);
+    const size_t bytes = p2p_window_bytes(world, slot_bytes);
+    B2_CUDA(cudaMalloc(&s->xwin, bytes));
+    B2_CUDA(cudaMemset(s->xwin, 0, bytes));
+    B2_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, s->xwin));
+    memcpy(handle_out, &h, sizeof(h));
+    s->x_world = world;
+    s->x_slot_bytes = slot_bytes;
+    s->x_epoch = 0;
+    return B200RAG_OK;
+}
+
+int b200rag_p2p_attach(b200rag_shard* sp, int32_t rank, int32_t world, const uint8_t* handles) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || handles == nullptr || s->xwin == nullptr || world != s->x_world || rank < 0 || rank >= world) {
+        set_error("p2p_attach: export a window of the same world size first");
+        return B200RAG_ERR_STATE;
+    }
+    B2_TRY(use_device(s));
+    s->x_rank = rank;
+    s->xpeers.assign((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { s->xpeers[(size_t)r] = s->xwin; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * B200RAG_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { p2p_release(s); return cuda_fail(e, "cudaIpcOpenMemHandle (peer exchange window)"); }
+        s->xpeers[(size_t)r] = ptr;
+    }
+    B2_TRY(s->ws.xpeers_dev.ensure((size_t)world * 8, 0, s->stream));
+    B2_CUDA(cudaMemcpyAsync(s->ws.xpeers_dev.p, s->xpeers.data(), (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B200RAG_OK;
+}
+
+int b200rag_p2p_exchange(b200rag_shard* sp, const void* mine, int64_t nbytes) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || mine == nullptr || s->xpeers.empty()) { set_error("p2p_exchange: no attached exchange window"); return B200RAG_ERR_STATE; }
+    if (nbytes <= 0 || nbytes % 16 != 0 || nbytes > s->x_slot_bytes) { set_error("p2p_exchange: block does not fit the exchange slot"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    ++s->x_epoch;
+    return launch_exchange(s, mine, nbytes, s->ws.xpeers_dev.as<void*>(), s->x_world, s->x_rank, s->x_slot_bytes,
+                           (int)(s->x_epoch & 1ull), s->x_epoch);
+}
+
+int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || out_ids == nullptr || out_scores == nullptr || out_counts == nullptr || s->xpeers.empty()) {
+        set_error("p2p_fuse: bad argument or no attached exchange window");
+        return B200RAG_ERR_INVALID;
+    }
+    if (!s->staged || s->x_epoch == 0) { set_error("p2p_fuse: stage + legs + exchange first"); return B200RAG_ERR_STATE; }
+    B2_TRY(use_device(s));
+    const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
+    const uint8_t* win = (const uint8_t*)s->xwin;
+    const b200rag_cand* gathered = (const b200rag_cand*)(win + (size_t)(s->x_epoch & 1ull) * s->x_world * s->x_slot_bytes);
+    const unsigned long long* flags = (const unsigned long long*)(win + (size_t)2 * s->x_world * s->x_slot_bytes);
+    return launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
+                       out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch);
+}
+
+int b200rag_p2p_close(b200rag_shard* sp) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    p2p_release(s);
     return B200RAG_OK;
 }
 

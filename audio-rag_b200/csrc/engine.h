@@ -65,6 +65,7 @@ struct Workspace {
     DevBuf lists_d;
     DevBuf exact2;
     DevBuf q_eps;         // [B] f32 absolute error bound of the sparse scan's approximate scores | [B] i32 grid-wide thresholds
+    DevBuf xpeers_dev;    // [world] void*: exchange windows of all ranks (peer pointers)
     DevBuf pool;          // filter path of the tcgen05 kernel: [B, cap] u64 keys | [B] i32 counters
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
@@ -133,6 +134,13 @@ struct Shard {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // dense scan begin/end, sparse scan begin/end
     bool ev_dense = false, ev_sparse = false;
 
+    // peer-memory exchange window (b200rag_p2p_*): [2 parities][world][slot_bytes] | [world] flags, 128 bytes apart
+    void* xwin = nullptr;
+    std::vector<void*> xpeers;            // every rank's window as seen from this device (own window at [rank])
+    int x_rank = 0, x_world = 0;
+    int64_t x_slot_bytes = 0;
+    unsigned long long x_epoch = 0;
+
     // pinned host staging for results
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -167,7 +175,12 @@ bool leg_tail_fits(int n_lists, int Lc);
 int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L, const uint64_t* lists, float eps_abs,
                     float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
-                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts);
+                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts,
+                int64_t shard_stride_override = 0, const unsigned long long* wait_flags = nullptr,
+                unsigned long long wait_epoch = 0);
+int launch_exchange(Shard* s, const void* mine, int64_t nbytes, void* const* peer_windows_dev, int world, int rank,
+                    int64_t slot_bytes, int parity, unsigned long long epoch);
+constexpr int kFlagStrideU64 = 16;   // exchange flags sit 128 bytes apart
 
 // ---- sparse.cu -----------------------------------------------------------------------------------------
 int build_inverted(Shard* s);

@@ -502,7 +502,8 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
                                                    int64_t shard_stride, int has_trailer, int nlegs, int batch,
                                                    int L, int top_k, int rrf_k,
                                                    int64_t* __restrict__ out_ids, double* __restrict__ out_scores,
-                                                   int32_t* __restrict__ out_counts) {
+                                                   int32_t* __restrict__ out_counts,
+                                                   const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const int M = n_shards * L;
     b200rag_cand* stage = reinterpret_cast<b200rag_cand*>(fsm);
@@ -516,6 +517,27 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
     const int q = blockIdx.x;
     if (threadIdx.x < 2) leg_n[threadIdx.x] = 0;
     if (threadIdx.x == 0) total_s = 0;
+    if (wait_flags != nullptr) {
+        // peer-memory exchange: every shard's block is complete once its flag carries this search's epoch
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
+        if (threadIdx.x < n_shards) {
+            const unsigned long long* f = wait_flags + (size_t)threadIdx.x * kFlagStrideU64;
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned long long v;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v >= wait_epoch) break;
+                if (clock64() - t0 > 4000000000ll) { timed_out = 1; break; }   // ~2 s: a peer is gone
+            }
+        }
+        __syncthreads();
+        if (timed_out) {
+            if (threadIdx.x == 0) { out_counts[q] = 0; if (q == 0) out_counts[batch] = -1; }
+            return;
+        }
+    }
     if (has_trailer && q == 0 && threadIdx.x == 0) {
         int amb = 0;
         for (int sh = 0; sh < n_shards; ++sh)
@@ -604,8 +626,35 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
     if (threadIdx.x == 0) out_counts[q] = n;
 }
 
+// every block p stores this rank's candidate block into slot `rank` of rank p's window, then publishes the epoch
+__global__ void __launch_bounds__(256) exchange_kernel(const uint4* __restrict__ mine, int64_t n16,
+                                                       void* const* __restrict__ peer_windows, int world, int rank,
+                                                       int64_t slot_bytes, int parity, unsigned long long epoch) {
+    const int pr = blockIdx.x;
+    uint8_t* win = reinterpret_cast<uint8_t*>(peer_windows[pr]);
+    uint4* dst = reinterpret_cast<uint4*>(win + ((size_t)parity * world + rank) * slot_bytes);
+    for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = mine[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(win + (size_t)2 * world * slot_bytes) +
+                                   (size_t)rank * kFlagStrideU64;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    }
+}
+
+int launch_exchange(Shard* s, const void* mine, int64_t nbytes, void* const* peer_windows_dev, int world, int rank,
+                    int64_t slot_bytes, int parity, unsigned long long epoch) {
+    exchange_kernel<<<world, 256, 0, s->stream>>>(reinterpret_cast<const uint4*>(mine), nbytes / 16, peer_windows_dev, world,
+                                                  rank, slot_bytes, parity, epoch);
+    B2_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return B200RAG_OK;
+}
+
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
-                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
+                int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts,
+                int64_t shard_stride_override, const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     const int nlegs = mode == B200RAG_HYBRID ? 2 : 1;
     const size_t M = (size_t)n_shards * L;
     const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
@@ -615,9 +664,10 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    const int64_t shard_stride = (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
+    const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
+                                                           : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
     fuse_kernel<<<batch, 256, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
-                                                 rrf_k, out_ids, out_scores, out_counts);
+                                                 rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;

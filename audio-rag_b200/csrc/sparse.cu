@@ -408,8 +408,13 @@ template <int NT, int EPT, int U>
 static int launch_scan_tu(Shard* s, const SparseScanParams& p, int batch) {
     const size_t smem = (size_t)EPT * NT * 4 + (size_t)p.sel_cap * 8 + (size_t)NT * 16 + 16 + (size_t)EPT * NT / 8;
     auto kern = p.masks != nullptr ? sparse_scan_kernel<NT, EPT, U, true> : sparse_scan_kernel<NT, EPT, U, false>;
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    static size_t attr_smem[2] = {0, 0};      // per instantiation and mask flavour
+    size_t& done = attr_smem[p.masks != nullptr ? 1 : 0];
+    if (smem > done) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        done = smem;
+    }
     dim3 grid((unsigned)batch, (unsigned)p.n_groups);
     kern<<<grid, NT, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());

@@ -253,6 +253,7 @@ def run_b200(a):
     sh.set_profiling(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     dense_ms, sparse_ms, launches, dense_bytes, postings = [], [], 0, 0, 0
+    dense_path, dense_passes = 1, 1
     barrier()
     if sampler:
         sampler.start()
@@ -272,6 +273,7 @@ def run_b200(a):
             dense_ms.append(st["dense_scan_ms"]); sparse_ms.append(st["sparse_scan_ms"])
             launches += st["kernel_launches"] + 1 + (1 if world > 1 else 0)   # + trailer memset (+ NCCL kernel)
             dense_bytes, postings = st["dense_bytes"], st["sparse_postings"]
+            dense_path, dense_passes = st["dense_path"], st["dense_passes"]
     barrier()
     wall_value = time.perf_counter() - wall0
     step_ms = np.array([s.elapsed_time(e) for s, e in ev], dtype=np.float64)
@@ -325,7 +327,35 @@ def run_b200(a):
                 traffic = None
         rows_rank = hi - lo
         algo_gb = rows_rank * a.dim * 2 / 1e9
-        achieved = algo_gb / (dense_k_ms / 1e3) if dense_k_ms > 0 else 0.0
+        # the dominant kernel: SIMT bulk scan (1-2 queries, one launch per corpus pass) or the tcgen05 GEMM (batches:
+        # one launch per pass of <= 256 queries).  Per-launch figures: bytes = rows * dim * 2, flops = 2 * q * rows * dim.
+        passes = max(int(dense_passes), 1)
+        launch_ms = dense_k_ms / passes
+        achieved = algo_gb / (launch_ms / 1e3) if dense_k_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": which}
+        if dense_path == 2:
+            tf_peak = 1413.9
+            try:
+                tf_peak = float(json.load(open(peaks_path)).get("bf16_tflops_sustained", tf_peak))
+            except Exception:
+                pass
+            q_per_launch = B / passes
+            tflops = 2.0 * q_per_launch * rows_rank * a.dim / (launch_ms / 1e3) / 1e12 if dense_k_ms > 0 else 0.0
+            roof["kernel"] = "dense_gemm_kernel (tcgen05; CTA pairs when more than 128 queries share a pass)"
+            roof["traffic"] = None
+            roof["hbm_GBps"], roof["hbm_frac"] = achieved, achieved / peak
+            roof["tensor_TFLOPs"], roof["tensor_frac"] = tflops, tflops / tf_peak
+            if tflops / tf_peak > achieved / peak:      # past the ridge: the tensor pipe is the binding roof
+                roof.update({"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": tflops / tf_peak,
+                             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"})
+        roof.update({"algorithmic_bytes_per_launch": int(rows_rank * a.dim * 2), "launches_per_step": passes,
+                     "kernel_ms": launch_ms, "kernel_share_of_step": dense_k_ms / (total_ms / K),
+                     "sparse_scan_ms": sparse_k_ms, "sparse_postings_per_step": int(postings),
+                     "sparse_algorithmic_GBps": postings * 6 / 1e9 / (sparse_k_ms / 1e3) if sparse_k_ms > 0 else 0.0,
+                     "step_algorithmic_GBps": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3),
+                     "step_frac": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3) / peak})
         qps = B * K / (total_ms / 1e3)
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -345,13 +375,7 @@ def run_b200(a):
                            "b200rag.dist.ShardedSearcher.search (host buffers; stage/legs/fuse C ABI + NCCL all-gather)",
                     "matches_device_path": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": which,
-                         "algorithmic_bytes_per_launch": int(rows_rank * a.dim * 2),
-                         "kernel_ms": dense_k_ms, "kernel_share_of_step": dense_k_ms / (total_ms / K),
-                         "sparse_scan_ms": sparse_k_ms, "sparse_postings_per_step": int(postings),
-                         "step_algorithmic_GBps": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3),
-                         "step_frac": (dense_bytes + postings * 6) / 1e9 / (total_ms / K / 1e3) / peak},
+            "roofline": roof,
             "clocks": clocks,
             "build_s": t_build, "ambiguous_flags": int(amb),
         }

@@ -135,7 +135,7 @@ int b200rag_search(b200rag_shard* s, const b200rag_query* q, int64_t* out_ids_ho
  *   stage : copy the query batch to the device (async on the shard's stream);
  *   legs  : per-shard candidates, exact-scored & ordered; cands_dev is [nlegs, batch, L] b200rag_cand with
  *           nlegs = 2 (dense, sparse) for HYBRID else 1, L = 2*top_k for HYBRID else top_k;
- *           ambiguous_dev (device int32, may be NULL) is incremented when a leg's slack guard fails;
+ *           ambiguous_dev (device int32, may be NULL) is zeroed, then incremented when a leg's slack guard fails;
  *   fuse  : merge `n_shards` gathered candidate sets [n_shards, nlegs, batch, L] under R5, then RRF under
  *           R9/R10 (HYBRID), writing device results [batch, top_k].
  * Exchange format: with has_trailer != 0 every shard's block is followed by ONE trailer b200rag_cand whose
@@ -147,6 +147,26 @@ int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L);
 int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
 int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int32_t has_trailer,
                  int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
+
+/* ---- peer-memory candidate exchange (one process per GPU, NVLink/NVSwitch P2P) ---------------------------------
+ * Replaces the NCCL all-gather between `legs` and `fuse` when every shard of a search sits on a GPU of the same box:
+ *   export  : allocate this shard's exchange window (2 parities x world slots of slot_bytes + flags) and return its
+ *             CUDA IPC handle (B200RAG_IPC_HANDLE_BYTES bytes) for the other ranks;
+ *   attach  : open the `world` handles (rank-ordered, own handle included) -> peer pointers;
+ *   exchange: ONE kernel stores this rank's candidate block (nbytes <= slot_bytes, trailer included) into slot `rank`
+ *             of EVERY rank's window with peer stores, then publishes the search's epoch to every rank's flag word
+ *             (release at system scope);
+ *   fuse    : b200rag_fuse on the local window; the kernel itself waits (acquire at system scope) until all `world`
+ *             flags carry the epoch, so there is no host synchronisation and no collective launch in the search.
+ * Every rank must make the same sequence of exchange/fuse calls (SPMD).  A rank may run at most one search ahead
+ * of its peers (its next fuse waits for their next epoch), which the two slot parities cover.  If a peer's flag does
+ * not arrive within ~2 s the fuse gives up and reports out_counts_dev[batch] = -1. */
+#define B200RAG_IPC_HANDLE_BYTES 64
+int b200rag_p2p_export(b200rag_shard* s, int32_t world, int64_t slot_bytes, uint8_t* handle_out);
+int b200rag_p2p_attach(b200rag_shard* s, int32_t rank, int32_t world, const uint8_t* handles);
+int b200rag_p2p_exchange(b200rag_shard* s, const void* mine_dev, int64_t nbytes);
+int b200rag_p2p_fuse(b200rag_shard* s, int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
+int b200rag_p2p_close(b200rag_shard* s);
 
 /* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
 typedef struct {

@@ -48,7 +48,7 @@ def main():
     tot = torch.tensor([bad], device=dev)
     dist.all_reduce(tot)
     if rank == 0:
-        print(f"dist_check world={world}: mismatches={int(tot.item())}", flush=True)
+        print(f"dist_check world={world} p2p={ss.p2p}: mismatches={int(tot.item())}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(1 if int(tot.item()) else 0)
