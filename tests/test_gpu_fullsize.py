@@ -122,3 +122,44 @@ def test_fullsize_properties(big):
     assert np.array_equal(h[:nq * k].reshape(nq, k), ids_h)
     assert np.array_equal(h[nq * k:2 * nq * k].view(np.float64).reshape(nq, k), sc_h)
     assert h[2 * nq * k:].view(np.int32)[nq] == 0
+
+
+def test_fullsize_batched_paths_agree_with_single_query_paths(big):
+    """At 10M rows every batched kernel must return, bit for bit, what the single-query kernels return:
+    tcgen05 on CTA pairs (160 queries, one pass of 256) vs the SIMT scan; the sample+filter epilogue (top-100) vs the
+    SIMT scan; the multi-block sparse scan with 24 queries in flight vs one query at a time; hybrid batches likewise."""
+    from b200rag import normalize_bf16, synth
+    one, _, _, _ = big
+    nq = 160
+    qf = synth.dense_queries_f32(2000, 100, nq, ROWS, 1024, corpus_seed=1234)
+    ip, tt, ww = synth.sparse_queries(2000, 100, nq)
+    qb = normalize_bf16(qf)
+
+    def single(mode, k, idx):
+        out = []
+        for i in idx:
+            r = one.search(mode, k, qb[i:i + 1], ip[i:i + 2] - ip[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]])
+            assert one.stats()["dense_path"] in (0, 1)
+            out.append((r[0][0], r[1][0], int(r[2][0])))
+        return out
+
+    probe = [0, 1, 77, 127, 128, 159]
+    # CTA pairs, register lists
+    ids, sc, cnt = one.search("dense", 10, qb)
+    assert one.stats()["dense_path"] == 2 and one.stats()["dense_passes"] == 1
+    for i, (ei, es, ec) in zip(probe, single("dense", 10, probe)):
+        assert cnt[i] == ec and np.array_equal(ids[i], ei) and np.array_equal(sc[i], es)
+    # sample + filter epilogue (top-100), also on pairs
+    ids, sc, cnt = one.search("dense", 100, qb)
+    assert one.stats()["dense_passes"] == 1 and one.stats()["retries"] == 0
+    for i, (ei, es, ec) in zip(probe[:3], single("dense", 100, probe[:3])):
+        assert cnt[i] == ec and np.array_equal(ids[i], ei) and np.array_equal(sc[i], es)
+    # sparse and hybrid batches
+    sl = slice(0, 24)
+    sip = ip[:25] - ip[0]
+    ids, sc, cnt = one.search("sparse", 10, qb[sl], sip, tt[:ip[24]], ww[:ip[24]])
+    for i, (ei, es, ec) in zip([0, 5, 23], single("sparse", 10, [0, 5, 23])):
+        assert cnt[i] == ec and np.array_equal(ids[i, :ec], ei[:ec]) and np.array_equal(sc[i, :ec], es[:ec])
+    ids, sc, cnt = one.search("hybrid", 10, qb[sl], sip, tt[:ip[24]], ww[:ip[24]])
+    for i, (ei, es, ec) in zip([0, 5, 23], single("hybrid", 10, [0, 5, 23])):
+        assert cnt[i] == ec and np.array_equal(ids[i, :ec], ei[:ec]) and np.array_equal(sc[i, :ec], es[:ec])

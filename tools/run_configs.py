@@ -108,10 +108,11 @@ def main():
             res.append(run(sh, dev, 10_000_000, "hybrid", 64, 10, 20, label="(extra) same without masks, B=64"))
         sh.close()
         torch.cuda.empty_cache()
-    if "c5" in only:       # hybrid top-100 over 100M on 8 GPUs: the per-GPU shard (12.5M rows), B = 1 and 128
+    if "c5" in only:       # hybrid top-100 over 100M on 8 GPUs: the per-GPU shard (12.5M rows), B = 1, 128 (dense leg) and 1024
         sh = shard(12_500_000, True, n_total=100_000_000)
         res.append(run(sh, dev, 100_000_000, "hybrid", 1, 100, 10, label="config5 hybrid top-100, per-GPU shard of 100M/8, B=1"))
         res.append(run(sh, dev, 100_000_000, "dense", 128, 100, 5, label="config5 dense leg top-100, per-GPU shard of 100M/8, B=128"))
+        res.append(run(sh, dev, 100_000_000, "hybrid", 1024, 100, 3, label="config5 hybrid top-100, per-GPU shard of 100M/8, B=1024"))
         sh.close()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump({"peaks": {"hbm_gbs": PEAK_HBM, "bf16_tflops_sustained": PEAK_TF}, "results": res,
