@@ -50,7 +50,8 @@ class Query(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int32), ("dense_path", C.c_int32), ("dense_bytes", C.c_int64),
                 ("sparse_postings", C.c_int64), ("dense_passes", C.c_int32), ("retries", C.c_int32),
-                ("dense_scan_ms", C.c_float), ("sparse_scan_ms", C.c_float)]
+                ("dense_scan_ms", C.c_float), ("sparse_scan_ms", C.c_float),
+                ("pre_scan_ms", C.c_float), ("tail_ms", C.c_float)]
 
 
 # every symbol include/b200rag.h declares: (name, restype, argtypes)

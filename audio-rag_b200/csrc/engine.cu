@@ -344,7 +344,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     s->ws.exact.release(); s->ws.pool.release(); s->ws.cands.release(); s->ws.out.release();
     s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release(); s->ws.q_eps.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
@@ -600,7 +600,8 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     if (!s->staged) { set_error("legs: no staged query batch"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
     s->stats = b200rag_stats{};
-    s->ev_dense = s->ev_sparse = false;
+    s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[4], s->stream)); s->ev_in = true; }
     if (ambiguous_dev != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));   // callers need not pre-zero it
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
@@ -615,8 +616,10 @@ int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int3
     if (!s->staged) { set_error("fuse: no staged query batch"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
     const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
-    return launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
-                       has_trailer, out_ids, out_scores, out_counts);
+    B2_TRY(launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
+                       has_trailer, out_ids, out_scores, out_counts));
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[5], s->stream)); s->ev_out = true; }
+    return B200RAG_OK;
 }
 
 int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, double* out_scores,
@@ -764,8 +767,10 @@ int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, in
     const uint8_t* win = (const uint8_t*)s->xwin;
     const b200rag_cand* gathered = (const b200rag_cand*)(win + (size_t)(s->x_epoch & 1ull) * s->x_world * s->x_slot_bytes);
     const unsigned long long* flags = (const unsigned long long*)(win + (size_t)2 * s->x_world * s->x_slot_bytes);
-    return launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
-                       out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch);
+    B2_TRY(launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
+                       out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch));
+    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[5], s->stream)); s->ev_out = true; }
+    return B200RAG_OK;
 }
 
 int b200rag_p2p_close(b200rag_shard* sp) {
@@ -792,6 +797,8 @@ int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
         float ms = 0.f;
         if (s->ev_dense && cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) s->stats.dense_scan_ms = ms;
         if (s->ev_sparse && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) s->stats.sparse_scan_ms = ms;
+        if (s->ev_in && s->ev_dense && cudaEventElapsedTime(&ms, s->ev[4], s->ev[0]) == cudaSuccess) s->stats.pre_scan_ms = ms;
+        if (s->ev_out && s->ev_dense && cudaEventElapsedTime(&ms, s->ev[1], s->ev[5]) == cudaSuccess) s->stats.tail_ms = ms;
         cudaGetLastError();
     }
     *out = s->stats;
@@ -803,9 +810,9 @@ int b200rag_set_profiling(b200rag_shard* sp, int32_t on) {
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
     if (on && s->ev[0] == nullptr)
-        for (int i = 0; i < 4; ++i) B2_CUDA(cudaEventCreate(&s->ev[i]));
+        for (int i = 0; i < 6; ++i) B2_CUDA(cudaEventCreate(&s->ev[i]));
     s->profile = on != 0;
-    s->ev_dense = s->ev_sparse = false;
+    s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     return B200RAG_OK;
 }
 

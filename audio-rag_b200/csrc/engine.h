@@ -131,8 +131,8 @@ struct Shard {
     Workspace ws;
     b200rag_stats stats{};
     bool profile = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // dense scan begin/end, sparse scan begin/end
-    bool ev_dense = false, ev_sparse = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // dense scan begin/end, sparse scan begin/end, legs entry, fuse end
+    bool ev_dense = false, ev_sparse = false, ev_in = false, ev_out = false;
 
     // peer-memory exchange window (b200rag_p2p_*): [2 parities][world][slot_bytes] | [world] flags, 128 bytes apart
     void* xwin = nullptr;

@@ -254,6 +254,7 @@ def run_b200(a):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     dense_ms, sparse_ms, launches, dense_bytes, postings = [], [], 0, 0, 0
     dense_path, dense_passes = 1, 1
+    pre_ms, tail_ms = [], []
     barrier()
     if sampler:
         sampler.start()
@@ -271,6 +272,7 @@ def run_b200(a):
             ev[i - W][1].record()
             st = sh.stats()                                               # syncs; outside the event bracket
             dense_ms.append(st["dense_scan_ms"]); sparse_ms.append(st["sparse_scan_ms"])
+            pre_ms.append(st["pre_scan_ms"]); tail_ms.append(st["tail_ms"])
             launches += st["kernel_launches"] + 1 + (1 if world > 1 else 0)   # + trailer memset (+ NCCL kernel)
             dense_bytes, postings = st["dense_bytes"], st["sparse_postings"]
             dense_path, dense_passes = st["dense_path"], st["dense_passes"]
@@ -376,6 +378,9 @@ def run_b200(a):
                     "matches_device_path": same},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "step_breakdown_ms": {"launch_to_scan": float(np.mean(pre_ms)), "dense_scan": float(np.mean(dense_ms)),
+                                  "scan_end_to_fuse_end": float(np.mean(tail_ms)),
+                                  "note": "rank 0, CUDA events inside the timed steps"},
             "clocks": clocks,
             "build_s": t_build, "ambiguous_flags": int(amb),
         }

@@ -178,6 +178,8 @@ typedef struct {
     int32_t retries;             /* slack-guard retries inside b200rag_search                              */
     float dense_scan_ms;         /* with profiling on: device time of the dense scan kernel(s) of the last legs */
     float sparse_scan_ms;        /* ... and of the sparse scan kernel (CUDA events on the shard's stream)      */
+    float pre_scan_ms;           /* ... from the entry of `legs` to the start of the dense scan (launch latency)  */
+    float tail_ms;               /* ... from the end of the dense scan to the end of the last `fuse`               */
 } b200rag_stats;
 int b200rag_get_stats(const b200rag_shard* s, b200rag_stats* out);
 /* Bracket the two scan kernels with CUDA events on the launching stream (bench.py's roofline figures). */
