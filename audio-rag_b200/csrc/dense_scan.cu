@@ -8,11 +8,10 @@
 // cp.async.bulk -> SASS UBLKCP) completing on mbarriers.  Measured on B200: a 3-stage ring filled in 8 KB pieces
 // (96 KB in flight per SM) reaches 6.7 TB/s, deeper rings are slower (6 stages: 6.2 TB/s).  Warps 1-8 consume: each
 // takes two rows of a tile, reads them with conflict-free 128-bit LDS, multiplies against the query held in
-// registers (fp32 FMA), butterfly-reduces, and streams the score into a warp-private top-Lc selection: a sorted
-// list spread over the warp's registers (ballot + shuffle insert) for Lc <= 64, else threshold + smem buffer +
-// in-warp bitonic compaction.  Thresholds are shared grid-wide through a monotone atomicMax so that after the
-// first few tiles almost no row passes the compare.  The score vector never reaches HBM; each CTA emits one sorted
-// list of Lc keys per query.
+// registers (fp32 FMA), butterfly-reduces, and appends scores above the running threshold to the CTA's candidate
+// buffer in shared memory, which all consumer warps compact together (bitonic, keep the best Lc) when it nears
+// capacity.  Thresholds are shared grid-wide through a monotone atomicMax so that after the first few tiles almost
+// no row passes the compare.  The score vector never reaches HBM; each CTA emits one sorted list of Lc keys per query.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = n_rows * dim * 2.
 #include "common.cuh"

@@ -7,19 +7,18 @@
 //
 // Index layout (block-major CSR): the shard's documents are cut into blocks of R consecutive local rows.
 // Block b owns   dir[b][0..V]   u32 offsets (a dense term directory: one lookup, no search)
-//                post_doc[]     u16 document offset inside the block      } SoA, 6 bytes per posting,
-//                post_w[]       f32 impact weight                          } term-major, doc ascending
+//                post_doc[]     u16 byte offset (4 * slot) of the document's accumulator   } SoA, 6 bytes per posting,
+//                post_w[]       f32 impact weight                                           } term-major, doc ascending
 // Appending rows only ever touches the trailing block, so the index is incremental by construction.
 //
-// Scan kernel: one CTA per (block, query).  fp32 accumulators for the block's R documents live in shared
-// memory (-0.0f == "untouched"); the query's terms are walked in ascending term id, each term's postings
-// segment streamed with aligned 128/256-bit loads and applied with plain (conflict-free within a term)
-// shared-memory read-modify-writes, so the summation order per document is deterministic.  The epilogue
-// applies the eligibility bitmask and selects the block's top-Lc without sorting the block: per-thread maxima
-// give a threshold, survivors are compacted and bitonic-sorted.  Nothing but Lc keys per (block, query)
-// reaches HBM.
+// Scan kernel: one CTA per (query, group of consecutive blocks), grid query-fastest.  int32 fixed-point accumulators
+// for a block's R documents live in shared memory; all query terms' posting vectors form ONE flat work list (no
+// barrier between terms): 128-bit offset loads + 256-bit weight loads, then native shared-memory integer atomics.
+// The epilogue applies the eligibility bitmask and keeps a running top-Lc across the CTA's blocks: one pass over the
+// accumulators against a threshold that is shared grid-wide per query.  Nothing but Lc keys per CTA reaches HBM.
 //
-// Roofline: HBM.  Algorithmic bytes = sum over query terms of df_shard(t) * 6  (SURVEY 8d counts 4+sizeof(w) = 8).
+// Roofline: HBM for the algorithmic bytes = sum over query terms of df_shard(t) * 6 (SURVEY 8d counts 4+sizeof(w) = 8);
+// measured binding unit: the L1/LSU data pipe (atomic wavefronts), see profiles/README.md.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
