@@ -83,6 +83,8 @@ SYMBOLS = [
     ("b200rag_legs_len", C.c_int, [C.POINTER(Query), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b200rag_legs", C.c_int, [_P, _P, _P]),
     ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    ("b200rag_save", C.c_int, [_P, C.c_char_p]),
+    ("b200rag_load", C.c_int, [_P, C.c_char_p]),
     ("b200rag_p2p_export", C.c_int, [_P, C.c_int32, C.c_int64, _P]),
     ("b200rag_p2p_attach", C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     ("b200rag_p2p_exchange", C.c_int, [_P, _P, C.c_int64]),
@@ -295,6 +297,12 @@ class Shard:
     def fuse(self, gathered_dev, n_shards, out_ids_dev, out_scores_dev, out_counts_dev, has_trailer=False):
         check(self._lib.b200rag_fuse(self._h, _ptr(gathered_dev), n_shards, 1 if has_trailer else 0, _ptr(out_ids_dev),
                                      _ptr(out_scores_dev), _ptr(out_counts_dev)))
+
+    def save(self, path: str):
+        check(self._lib.b200rag_save(self._h, os.fsencode(path)))
+
+    def load(self, path: str):
+        check(self._lib.b200rag_load(self._h, os.fsencode(path)))
 
     # ---- peer-memory candidate exchange (replaces the all-gather between legs and fuse on one box)
     IPC_HANDLE_BYTES = 64

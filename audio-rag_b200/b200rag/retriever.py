@@ -17,6 +17,8 @@ Additive API (no reference counterpart): ``search_batch``.
 """
 from __future__ import annotations
 
+import json
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -339,6 +341,69 @@ class B200Retriever(BaseRetriever):
             logger.info(f"Deleted collection: {resolved}")
         except Exception as e:
             raise RetrievalError(f"Failed to delete collection '{resolved}': {e}")
+
+    # ------------------------------------------------------------------ persistence (additive)
+    # The reference keeps its index in Qdrant's volume (docker-compose.yml:36-37).  Here a retriever is three files:
+    #   shard.bin       rows + forward sparse index (b200rag_save; the inverted index is rebuilt on load)
+    #   payloads.jsonl  one payload per row, insertion order (row id = line number, rule R1)
+    #   manifest.json   collections (ids, hybrid flags, live counts), row -> collection, tombstones, geometry
+    def save(self, directory: str) -> None:
+        try:
+            os.makedirs(directory, exist_ok=True)
+            self._get_shard().save(os.path.join(directory, "shard.bin"))
+            with open(os.path.join(directory, "payloads.jsonl"), "w", encoding="utf-8") as f:
+                for p in self._payloads:
+                    f.write(json.dumps(p, ensure_ascii=False) + "\n")
+            manifest = {
+                "format": "b200rag-retriever-1", "embedding_dim": self.embedding_dim, "vocab": self._vocab,
+                "row_base": self._row_base, "rows": len(self._payloads),
+                "collections": {name: {"id": cid, "hybrid": name in self._hybrid_collections,
+                                       "exists": name in self._existing_collections,
+                                       "live_rows": self._coll_rows.get(name, 0)}
+                                for name, cid in self._coll_ids.items()},
+                "row_collection": self._row_coll, "alive": [int(a) for a in self._alive],
+            }
+            with open(os.path.join(directory, "manifest.json"), "w", encoding="utf-8") as f:
+                json.dump(manifest, f)
+        except Exception as e:
+            raise RetrievalError(f"Failed to save retriever to '{directory}': {e}")
+
+    def load(self, directory: str) -> None:
+        """Restore a saved retriever into this (empty) one; config/embedding_dim/vocab must match the saved ones."""
+        try:
+            if self._payloads:
+                raise RetrievalError("load() needs an empty retriever")
+            with open(os.path.join(directory, "manifest.json"), encoding="utf-8") as f:
+                m = json.load(f)
+            if m.get("format") != "b200rag-retriever-1" or m["embedding_dim"] != self.embedding_dim or \
+                    m["vocab"] != self._vocab:
+                raise RetrievalError("manifest does not match this retriever (format, embedding_dim or vocab)")
+            with open(os.path.join(directory, "payloads.jsonl"), encoding="utf-8") as f:
+                payloads = [json.loads(line) for line in f]
+            if len(payloads) != m["rows"] or len(m["row_collection"]) != m["rows"] or len(m["alive"]) != m["rows"]:
+                raise RetrievalError("payloads.jsonl / manifest.json row counts disagree")
+            shard = self._get_shard()
+            shard.load(os.path.join(directory, "shard.bin"))
+            if shard.count != m["rows"]:
+                shard.clear()
+                raise RetrievalError("shard.bin holds a different number of rows than the manifest")
+            self._row_base = m["row_base"]
+            self._payloads = payloads
+            self._row_coll = [int(c) for c in m["row_collection"]]
+            self._alive = [bool(a) for a in m["alive"]]
+            for name, c in m["collections"].items():
+                self._coll_ids[name] = int(c["id"])
+                self._coll_rows[name] = int(c["live_rows"])
+                self._coll_version[name] = self._coll_version.get(name, 0) + 1
+                if c["exists"]:
+                    self._existing_collections.add(name)
+                if c["hybrid"]:
+                    self._hybrid_collections.add(name)
+            self._masks.clear()
+        except RetrievalError as e:
+            raise RetrievalError(f"Failed to load retriever from '{directory}': {e}")
+        except Exception as e:
+            raise RetrievalError(f"Failed to load retriever from '{directory}': {e}")
 
     def count(self, collection_name: str | None = None) -> int:
         resolved = self._ensure_collection(collection_name)

@@ -7,6 +7,8 @@
 #include <string>
 
 #include "common.cuh"
+#include <cstdio>
+
 #include "engine.h"
 
 namespace b200rag {
@@ -679,6 +681,93 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
 }
 
 }  // extern "C"
+
+// ---- persistence -------------------------------------------------------------------------------------------------
+struct ShardFileHeader {
+    char magic[8];            // "B200RAG1"
+    int32_t version, dim, vocab, reserved;
+    int64_t n_rows, nnz;
+};
+
+static int dev_to_file(Shard* s, const void* dev, size_t bytes, FILE* f, void* stage, size_t stage_bytes) {
+    for (size_t o = 0; o < bytes; o += stage_bytes) {
+        const size_t n = std::min(stage_bytes, bytes - o);
+        B2_CUDA(cudaMemcpyAsync(stage, (const uint8_t*)dev + o, n, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        if (fwrite(stage, 1, n, f) != n) { set_error("save: short write"); return B200RAG_ERR_INVALID; }
+    }
+    return B200RAG_OK;
+}
+
+static int file_to_dev(Shard* s, void* dev, size_t bytes, FILE* f, void* stage, size_t stage_bytes) {
+    for (size_t o = 0; o < bytes; o += stage_bytes) {
+        const size_t n = std::min(stage_bytes, bytes - o);
+        if (fread(stage, 1, n, f) != n) { set_error("load: file is truncated"); return B200RAG_ERR_INVALID; }
+        B2_CUDA(cudaMemcpyAsync((uint8_t*)dev + o, stage, n, cudaMemcpyHostToDevice, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return B200RAG_OK;
+}
+
+extern "C" int b200rag_save(b200rag_shard* sp, const char* path) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || path == nullptr) { set_error("save: null argument"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    FILE* f = fopen(path, "wb");
+    if (f == nullptr) { set_error(std::string("save: cannot open ") + path); return B200RAG_ERR_INVALID; }
+    ShardFileHeader h{};
+    memcpy(h.magic, "B200RAG1", 8);
+    h.version = 1; h.dim = s->dim; h.vocab = s->vocab; h.n_rows = s->n_rows; h.nnz = s->nnz;
+    const size_t stage_bytes = (size_t)64 << 20;
+    void* stage = nullptr;
+    int rc = B200RAG_OK;
+    if (cudaMallocHost(&stage, stage_bytes) != cudaSuccess) { cudaGetLastError(); fclose(f); set_error("save: no pinned staging memory"); return B200RAG_ERR_CUDA; }
+    if (fwrite(&h, sizeof(h), 1, f) != 1) { set_error("save: short write"); rc = B200RAG_ERR_INVALID; }
+    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->dense.p, (size_t)s->n_rows * s->dim * 2, f, stage, stage_bytes);
+    if (rc == B200RAG_OK) rc = dev_to_file(s, s->fwd_ptr.p, (size_t)(s->n_rows + 1) * 8, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_terms.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_w.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
+    cudaFreeHost(stage);
+    if (fclose(f) != 0 && rc == B200RAG_OK) { set_error("save: close failed"); rc = B200RAG_ERR_INVALID; }
+    return rc;
+}
+
+extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || path == nullptr) { set_error("load: null argument"); return B200RAG_ERR_INVALID; }
+    if (s->n_rows != 0) { set_error("load: the shard must be empty"); return B200RAG_ERR_STATE; }
+    B2_TRY(use_device(s));
+    FILE* f = fopen(path, "rb");
+    if (f == nullptr) { set_error(std::string("load: cannot open ") + path); return B200RAG_ERR_INVALID; }
+    ShardFileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "B200RAG1", 8) != 0 || h.version != 1) {
+        fclose(f); set_error("load: not a b200rag shard file"); return B200RAG_ERR_INVALID;
+    }
+    if (h.dim != s->dim || h.vocab != s->vocab || h.n_rows < 0 || h.nnz < 0 || h.n_rows > 0xFFFFFFF0ll) {
+        fclose(f); set_error("load: file was written for another dim/vocab"); return B200RAG_ERR_INVALID;
+    }
+    const size_t stage_bytes = (size_t)64 << 20;
+    void* stage = nullptr;
+    if (cudaMallocHost(&stage, stage_bytes) != cudaSuccess) { cudaGetLastError(); fclose(f); set_error("load: no pinned staging memory"); return B200RAG_ERR_CUDA; }
+    cudaStream_t st = s->stream;
+    int rc = s->dense.ensure((size_t)std::max<int64_t>(h.n_rows, 1) * s->dim * 2, 0, st);
+    if (rc == B200RAG_OK) rc = s->fwd_ptr.ensure((size_t)(h.n_rows + 1) * 8, 0, st);
+    if (rc == B200RAG_OK) rc = s->fwd_terms.ensure((size_t)(h.nnz + 1) * 4, 0, st);
+    if (rc == B200RAG_OK) rc = s->fwd_w.ensure((size_t)(h.nnz + 1) * 4, 0, st);
+    if (rc == B200RAG_OK && h.n_rows > 0) rc = file_to_dev(s, s->dense.p, (size_t)h.n_rows * s->dim * 2, f, stage, stage_bytes);
+    if (rc == B200RAG_OK) rc = file_to_dev(s, s->fwd_ptr.p, (size_t)(h.n_rows + 1) * 8, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_terms.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_w.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
+    cudaFreeHost(stage);
+    fclose(f);
+    if (rc != B200RAG_OK) { s->n_rows = 0; s->nnz = 0; return rc; }
+    s->n_rows = h.n_rows;
+    s->nnz = h.nnz;
+    s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0; s->w_absmax = 0.f; s->wmax_nnz = 0;
+    s->h_blk_base.clear();
+    return build_inverted(s);
+}
 
 // ---- peer-memory exchange --------------------------------------------------------------------------------------
 static void p2p_release(Shard* s) {

@@ -148,6 +148,14 @@ int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
 int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int32_t has_trailer,
                  int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
 
+/* ---- persistence (the reference relies on Qdrant's volume, docker-compose.yml:36-37) -------------------------------
+ * One file per shard: header | dense bf16 rows | forward sparse index (indptr, terms, weights).  The inverted index,
+ * directories and the weight bound are rebuilt on load (~0.2 s per 10M rows) so the file has no layout the kernels
+ * depend on.  `load` needs an EMPTY shard created with the same dim and vocab; masks and payloads are the plugin's
+ * (B200Retriever.save/load write them next to this file).  Returns B200RAG_ERR_INVALID on a foreign/corrupt file. */
+int b200rag_save(b200rag_shard* s, const char* path);
+int b200rag_load(b200rag_shard* s, const char* path);
+
 /* ---- peer-memory candidate exchange (one process per GPU, NVLink/NVSwitch P2P) ---------------------------------
  * Replaces the NCCL all-gather between `legs` and `fuse` when every shard of a search sits on a GPU of the same box:
  *   export  : allocate this shard's exchange window (2 parities x world slots of slot_bytes + flags) and return its

@@ -76,3 +76,48 @@ def test_adapter_gpu_vs_oracle_twin(gpu):
         real.delete_collection(name)
     assert real._shard.count == 0
     real.close()
+
+
+def test_save_load_round_trip(gpu, tmp_path):
+    """Persistence: a saved retriever restored into a fresh one answers every search identically
+    (ids, scores, payloads), keeps collection schemas, tombstones and counts, and accepts further adds."""
+    A, E, S = _types()
+    r = _retriever(gpu, top_k=6)
+    data = {"t1": make_chunks(600, 41, "T1", A, E, S), "t2": make_chunks(250, 42, "T2", A, E, S),
+            "old": make_chunks(120, 43, "O", A, E, S, sparse=False), "gone": make_chunks(90, 45, "G", A, E, S)}
+    for name, (ch, em) in data.items():
+        r.add(ch, em, name)
+    r.delete_collection("gone")
+    qs = make_queries(4, 51, 600, 41, E, S)
+
+    def snapshot(x):
+        out = []
+        for st in ("dense", "sparse", "hybrid"):
+            for name in ("t1", "t2", "old", "gone"):
+                for flt in (None, {"lang": "en"}):
+                    for q in qs:
+                        out.append(result_rows(x.search(q, collection_name=name, search_type=st, filter_metadata=flt)))
+        return out
+
+    before = snapshot(r)
+    d = str(tmp_path / "idx")
+    r.save(d)
+    assert sorted(os.listdir(d)) == ["manifest.json", "payloads.jsonl", "shard.bin"]
+    r2 = _retriever(gpu, top_k=6)
+    r2.load(d)
+    assert snapshot(r2) == before
+    assert [r2.count(n) for n in ("t1", "t2", "old")] == [600, 250, 120]
+    assert r2.is_hybrid_collection("t1") and not r2.is_hybrid_collection("old")
+    # (searching a deleted name re-creates it empty, like the reference: qdrant.py:248) -> same state on both sides
+    assert r2.collection_exists("gone") == r.collection_exists("gone") and r2.count("gone") == 0
+    ch, em = make_chunks(40, 46, "T2b", A, E, S)
+    r.add(ch, em, "t2"); r2.add(ch, em, "t2")
+    assert snapshot(r2) == snapshot(r)
+    # a foreign file is refused
+    from b200rag.compat import RetrievalError
+    open(os.path.join(d, "shard.bin"), "wb").write(b"not a shard file at all")
+    r3 = _retriever(gpu, top_k=6)
+    with pytest.raises(RetrievalError):
+        r3.load(d)
+    for x in (r, r2, r3):
+        x.close()
