@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const Dense
     // SH: sort the CTA's buffer of query q (all consumer warps), keep the best Lc, publish the new threshold
     auto compact_shared = [&](int q) {
         const int n = ccnt[q];
+        const int np2 = next_pow2(n > p.Lc ? n : p.Lc);     // sort only what is there (the final compaction is short)
         named_bar_sync(1, NCT);
-        for (int i = n + ctid; i < p.cap; i += NCT) mybuf[q][i] = 0;
-        cta_bitonic_desc(mybuf[q], p.cap, ctid, NCT, 1);
+        for (int i = n + ctid; i < np2; i += NCT) mybuf[q][i] = 0;
+        cta_bitonic_desc(mybuf[q], np2, ctid, NCT, 1);
         if (ctid == 0) {
             if (n > p.Lc) ccnt[q] = p.Lc;
             const uint64_t nt = mybuf[q][p.Lc - 1];

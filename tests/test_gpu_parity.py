@@ -366,3 +366,55 @@ def test_gemm_filter_path_retry_and_robust_lists(gpu):
     assert st["retries"] == 0
     sh.set_slack(0)
     sh.close()
+
+
+@pytest.mark.parametrize("R", [1024, 16384])
+def test_sparse_fixed_point_edge_cases(gpu, R):
+    """The sparse scan accumulates in fixed point with integer atomics: mixed-sign weights (documents AND queries),
+    weights spanning 6 orders of magnitude, zero weights (touched, score 0), exact score ties across thousands of
+    documents (bisection fallback), long queries (count bits), several blocks per CTA -- ids and scores must stay
+    bit-equal to the oracle."""
+    from b200rag import Shard
+    rng = np.random.default_rng(R)
+    n, vocab, dim = 6000, 400, 256
+    c = Corpus(n, dim=dim, sparse=False)
+    nnz_per = rng.integers(0, 40, size=n)
+    indptr = np.concatenate([[0], np.cumsum(nnz_per)]).astype(np.int64)
+    terms = np.concatenate([np.sort(rng.choice(vocab, size=k, replace=False)) for k in nnz_per]).astype(np.uint32)
+    mag = 10.0 ** rng.uniform(-3, 3, size=len(terms))
+    w = (mag * rng.choice([-1.0, 1.0], size=len(terms))).astype(np.float32)
+    w[rng.random(len(terms)) < 0.05] = 0.0
+    # documents 100..3099 carry the SAME single posting: thousands of exact ties
+    tie_rows = np.arange(100, 3100)
+    for r in tie_rows:
+        s, e = indptr[r], indptr[r + 1]
+        if e > s:
+            terms[s:e] = np.sort(rng.choice(np.arange(1, vocab), size=e - s, replace=False))
+            terms[s], w[s] = 0, 0.75
+            w[s + 1:e] = 0.0
+    c.indptr, c.terms, c.w, c.vocab = indptr, terms, w, vocab
+    sh = Shard(dim=dim, vocab=vocab, device=gpu, docs_per_block=R)
+    sh.add(c.bits, indptr, terms, w)
+    qb = __import__("b200rag").normalize_bf16(c.queries(1)[0])
+    cases = [
+        (np.array([0], np.uint32), np.array([2.0], np.float32)),                                  # the tie term alone
+        (np.arange(0, vocab, 3, dtype=np.uint32), rng.normal(size=len(range(0, vocab, 3))).astype(np.float32)),
+        (np.arange(vocab, dtype=np.uint32), (10.0 ** rng.uniform(-2, 2, size=vocab)).astype(np.float32)),  # 400 terms
+        (np.array([5, 17, 200], np.uint32), np.array([-3.0, 0.0, 1e-3], np.float32)),
+    ]
+    for qi, (qt, qw) in enumerate(cases):
+        for k in (5, 100):
+            ids, scores, counts = sh.search("sparse", k, None, np.array([0, len(qt)], np.int64), qt, qw)
+            ei, es = oracle_search(c, "sparse", None, qt, qw, None, k)
+            assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx=f"R={R} case {qi} k={k}")
+    # a batch mixing all of them (different scales per query in one launch) + a hybrid with the dense leg
+    ip = np.concatenate([[0], np.cumsum([len(t) for t, _ in cases])]).astype(np.int64)
+    tt = np.concatenate([t for t, _ in cases]); ww = np.concatenate([x for _, x in cases])
+    ids, scores, counts = sh.search("sparse", 20, None, ip, tt, ww)
+    for qi, (qt, qw) in enumerate(cases):
+        ei, es = oracle_search(c, "sparse", None, qt, qw, None, 20)
+        assert_result_equal(ids[qi], scores[qi], int(counts[qi]), ei, es, ctx=f"R={R} batch case {qi}")
+    ids, scores, counts = sh.search("hybrid", 10, qb, np.array([0, len(cases[1][0])], np.int64), cases[1][0], cases[1][1])
+    ei, es = oracle_search(c, "hybrid", qb[0], cases[1][0], cases[1][1], None, 10)
+    assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx=f"R={R} hybrid")
+    sh.close()
