@@ -80,6 +80,8 @@ SYMBOLS = [
     ("b200rag_mask_drop", C.c_int, [_P, C.c_int32]),
     ("b200rag_search", C.c_int, [_P, C.POINTER(Query), _P, _P, _P]),
     ("b200rag_stage", C.c_int, [_P, C.POINTER(Query)]),
+    ("b200rag_stage_slot", C.c_int, [_P, C.POINTER(Query), C.c_int32]),
+    ("b200rag_use_slot", C.c_int, [_P, C.c_int32]),
     ("b200rag_legs_len", C.c_int, [C.POINTER(Query), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b200rag_legs", C.c_int, [_P, _P, _P]),
     ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
@@ -91,6 +93,7 @@ SYMBOLS = [
     ("b200rag_p2p_fuse", C.c_int, [_P, _P, _P, _P]),
     ("b200rag_p2p_close", C.c_int, [_P]),
     ("b200rag_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("b200rag_get_stats_step", C.c_int, [_P, C.c_int32, C.POINTER(Stats)]),
     ("b200rag_set_profiling", C.c_int, [_P, C.c_int32]),
     ("b200rag_synth_dense", C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P]),
     ("b200rag_synth_sparse", C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, C.c_int64,
@@ -281,9 +284,14 @@ class Shard:
         del keep
         return ids, scores, counts
 
-    def stage(self, q: Query, keep=None):
+    def stage(self, q: Query, keep=None, slot: int = 0):
+        """Copy a query batch to the device (its own block per `slot`) and make it the active one."""
         self._keep = keep
-        check(self._lib.b200rag_stage(self._h, C.byref(q)))
+        check(self._lib.b200rag_stage_slot(self._h, C.byref(q), slot))
+
+    def use_slot(self, slot: int):
+        """Re-activate an already staged batch (no copy, no synchronisation)."""
+        check(self._lib.b200rag_use_slot(self._h, slot))
 
     @staticmethod
     def legs_len(q: Query):
@@ -333,6 +341,12 @@ class Shard:
         st = Stats()
         check(self._lib.b200rag_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    def stats_step(self, steps_back: int) -> dict:
+        """Event timings (the *_ms fields) of the legs call made `steps_back` calls ago; profiling must be on."""
+        st = Stats()
+        check(self._lib.b200rag_get_stats_step(self._h, steps_back, C.byref(st)))
+        return {k: getattr(st, k) for k in ("dense_scan_ms", "sparse_scan_ms", "pre_scan_ms", "tail_ms")}
 
     # ---- synthetic generation on the device
     def synth_dense(self, seed, global_row_start, n, out_dev):

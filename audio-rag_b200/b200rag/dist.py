@@ -45,6 +45,7 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs: dict = {}
+        self._slots: dict = {}
         self.p2p = False
         self.p2p_slot_bytes = int(os.environ.get("B200RAG_P2P_SLOT_BYTES", 8 << 20))
         if self.world > 1 and device.type == "cuda" and hasattr(shard, "p2p_export") and \
@@ -102,12 +103,24 @@ class ShardedSearcher:
         return obj[0]
 
     def stage(self, mode, top_k, q_bits=None, sp_indptr=None, sp_terms=None, sp_weights=None, mask_ids=None,
-              score_threshold=None, rrf_k=0):
+              score_threshold=None, rrf_k=0, slot=None):
+        """Copy a query batch to the device.  With `slot` the batch gets its own device block and stays resident:
+        `use_slot(slot)` re-activates it later without a copy (a queue of batches enqueued back to back)."""
         q, keep = self.shard.make_query(mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids,
                                         score_threshold, rrf_k)
-        self.shard.stage(q, keep)
+        if slot is None:
+            self.shard.stage(q, keep)
+        else:
+            self.shard.stage(q, keep, slot=slot)
         nlegs, L = Shard.legs_len(q)
         self._cur = (nlegs, q.batch, L, top_k)
+        if slot is not None:
+            self._slots[slot] = self._cur
+        return self._cur
+
+    def use_slot(self, slot):
+        self.shard.use_slot(slot)
+        self._cur = self._slots[slot]
         return self._cur
 
     def run_staged(self):

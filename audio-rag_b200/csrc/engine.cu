@@ -342,12 +342,14 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     s->dense.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
-    s->ws.q_stage.release(); s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
+    for (auto& sl : s->slots) sl.buf.release();
+    s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
     s->ws.exact.release(); s->ws.pool.release(); s->ws.cands.release(); s->ws.out.release();
     s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release(); s->ws.q_eps.release();
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
-    for (int i = 0; i < 6; ++i)
-        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int r = 0; r < kProfileRing; ++r)
+        for (int i = 0; i < 6; ++i)
+            if (s->ev_ring[r][i]) cudaEventDestroy(s->ev_ring[r][i]);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -457,6 +459,7 @@ int b200rag_clear(b200rag_shard* sp) {
     s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->h_blk_base.clear();
     s->staged = false;
+    for (auto& sl : s->slots) sl.staged = false;
     for (auto& kv : s->masks) kv.second.release();
     s->masks.clear(); s->mask_rows.clear();
     return B200RAG_OK;
@@ -478,6 +481,8 @@ static int mask_store(Shard* s, int32_t id, const uint32_t* words, int64_t n_row
     const int64_t cover = std::max<int64_t>(((std::max(n_rows, s->n_rows) + 32767) / 32768) * 32768, 32768);
     const size_t words_total = (size_t)(cover / 32);
     const size_t words_in = (size_t)((n_rows + 31) / 32);
+    for (auto& sl : s->slots) sl.staged = false;     // staged batches hold raw mask pointers
+    s->staged = false;
     DevBuf& b = s->masks[id];
     B2_TRY(b.ensure(words_total * 4, 0, s->stream));
     B2_CUDA(cudaMemsetAsync(b.p, 0, b.cap, s->stream));
@@ -503,6 +508,8 @@ int b200rag_mask_drop(b200rag_shard* sp, int32_t id) {
     if (it == s->masks.end()) return B200RAG_OK;
     use_device(s);
     cudaStreamSynchronize(s->stream);
+    for (auto& sl : s->slots) sl.staged = false;
+    s->staged = false;
     it->second.release();
     s->masks.erase(it);
     s->mask_rows.erase(id);
@@ -516,9 +523,34 @@ int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L) {
     return B200RAG_OK;
 }
 
-int b200rag_stage(b200rag_shard* sp, const b200rag_query* q) {
+static void activate_slot(Shard* s, const QuerySlot& sl) {
+    s->ws.q_bits.p = sl.bits;
+    s->ws.q_sp_indptr.p = sl.ind;
+    s->ws.q_sp_terms.p = sl.terms;
+    s->ws.q_sp_w.p = sl.w;
+    s->ws.q_masks.p = sl.masks;
+    s->q = sl.q;
+    s->h_masks = sl.h_masks;
+    s->staged_q_terms = sl.q_terms;
+    s->staged = true;
+}
+
+int b200rag_stage(b200rag_shard* sp, const b200rag_query* q) { return b200rag_stage_slot(sp, q, 0); }
+
+int b200rag_use_slot(b200rag_shard* sp, int32_t slot) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || slot < 0 || slot >= (int)s->slots.size() || !s->slots[(size_t)slot].staged) {
+        set_error("use_slot: no batch staged in this slot");
+        return B200RAG_ERR_STATE;
+    }
+    activate_slot(s, s->slots[(size_t)slot]);
+    return B200RAG_OK;
+}
+
+int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || q == nullptr) { set_error("stage: null argument"); return B200RAG_ERR_INVALID; }
+    if (slot < 0 || slot >= 4096) { set_error("stage: slot out of range"); return B200RAG_ERR_INVALID; }
     if (q->mode < 0 || q->mode > 2) { set_error("stage: bad mode"); return B200RAG_ERR_INVALID; }
     if (q->batch < 1 || q->batch > 65535) { set_error("stage: batch must be in [1, 65535]"); return B200RAG_ERR_INVALID; }
     if (q->top_k < 1 || q->top_k > B200RAG_MAX_TOPK) { set_error("stage: top_k out of range"); return B200RAG_ERR_INVALID; }
@@ -565,7 +597,9 @@ int b200rag_stage(b200rag_shard* sp, const b200rag_query* q) {
     const size_t o_masks = al256(o_w + (size_t)nt * 4);
     const size_t total = al256(o_masks + (size_t)B * 8);
     B2_TRY(ensure_pinned(s, total + (size_t)B * q->top_k * 16 + (size_t)(B + 1) * 4 + 1024));
-    B2_TRY(s->ws.q_stage.ensure(total, 0, s->stream));
+    if ((size_t)slot >= s->slots.size()) s->slots.resize((size_t)slot + 1);
+    QuerySlot& sl = s->slots[(size_t)slot];
+    B2_TRY(sl.buf.ensure(total, 0, s->stream));
     // the previous batch's H2D must have drained before the pinned block is rewritten
     B2_CUDA(cudaStreamSynchronize(s->stream));
     uint8_t* h = (uint8_t*)s->h_pinned;
@@ -581,18 +615,20 @@ int b200rag_stage(b200rag_shard* sp, const b200rag_query* q) {
     }
     if (any_mask) memcpy(h + o_masks, s->h_masks.data(), (size_t)B * 8);
     else memset(h + o_masks, 0, (size_t)B * 8);
-    B2_CUDA(cudaMemcpyAsync(s->ws.q_stage.p, h, total, cudaMemcpyHostToDevice, s->stream));
-    uint8_t* d = s->ws.q_stage.as<uint8_t>();
-    s->ws.q_bits.p = d + o_bits;
-    s->ws.q_sp_indptr.p = d + o_ind;
-    s->ws.q_sp_terms.p = d + o_terms;
-    s->ws.q_sp_w.p = d + o_w;
-    s->ws.q_masks.p = d + o_masks;
-    s->q = *q;
-    if (s->q.rrf_k <= 0) s->q.rrf_k = 2;
-    s->q.q_dense_bits = nullptr; s->q.q_sp_indptr = nullptr; s->q.q_sp_terms = nullptr; s->q.q_sp_weights = nullptr; s->q.mask_ids = nullptr;
-    s->staged_q_terms = nt;
-    s->staged = true;
+    B2_CUDA(cudaMemcpyAsync(sl.buf.p, h, total, cudaMemcpyHostToDevice, s->stream));
+    uint8_t* d = sl.buf.as<uint8_t>();
+    sl.bits = d + o_bits;
+    sl.ind = d + o_ind;
+    sl.terms = d + o_terms;
+    sl.w = d + o_w;
+    sl.masks = d + o_masks;
+    sl.q = *q;
+    if (sl.q.rrf_k <= 0) sl.q.rrf_k = 2;
+    sl.q.q_dense_bits = nullptr; sl.q.q_sp_indptr = nullptr; sl.q.q_sp_terms = nullptr; sl.q.q_sp_weights = nullptr; sl.q.mask_ids = nullptr;
+    sl.h_masks = s->h_masks;
+    sl.q_terms = nt;
+    sl.staged = true;
+    activate_slot(s, sl);
     return B200RAG_OK;
 }
 
@@ -602,6 +638,12 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     if (!s->staged) { set_error("legs: no staged query batch"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
     s->stats = b200rag_stats{};
+    if (s->profile && s->legs_calls > 0) {      // keep the previous call's flags with its event set
+        bool* f = s->ev_flags[(s->legs_calls - 1) % kProfileRing];
+        f[0] = s->ev_dense; f[1] = s->ev_sparse; f[2] = s->ev_in; f[3] = s->ev_out;
+    }
+    s->ev = s->ev_ring[s->legs_calls % kProfileRing];
+    ++s->legs_calls;
     s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[4], s->stream)); s->ev_in = true; }
     if (ambiguous_dev != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));   // callers need not pre-zero it
@@ -894,12 +936,33 @@ int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
     return B200RAG_OK;
 }
 
+int b200rag_get_stats_step(const b200rag_shard* sp, int32_t steps_back, b200rag_stats* out) {
+    if (sp == nullptr || out == nullptr || steps_back < 0 || steps_back >= kProfileRing) { set_error("get_stats_step: bad argument"); return B200RAG_ERR_INVALID; }
+    Shard* s = (Shard*)sp;
+    *out = b200rag_stats{};
+    if (!s->profile || s->legs_calls <= steps_back) { set_error("get_stats_step: profiling is off or no such call"); return B200RAG_ERR_STATE; }
+    if (cudaSetDevice(s->cfg.device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "get_stats_step");
+    const int64_t call = s->legs_calls - 1 - steps_back;
+    cudaEvent_t* ev = s->ev_ring[call % kProfileRing];
+    bool f[4];
+    if (steps_back == 0) { f[0] = s->ev_dense; f[1] = s->ev_sparse; f[2] = s->ev_in; f[3] = s->ev_out; }
+    else { const bool* g = s->ev_flags[call % kProfileRing]; f[0] = g[0]; f[1] = g[1]; f[2] = g[2]; f[3] = g[3]; }
+    float ms = 0.f;
+    if (f[0] && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out->dense_scan_ms = ms;
+    if (f[1] && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) out->sparse_scan_ms = ms;
+    if (f[2] && f[0] && cudaEventElapsedTime(&ms, ev[4], ev[0]) == cudaSuccess) out->pre_scan_ms = ms;
+    if (f[3] && f[0] && cudaEventElapsedTime(&ms, ev[1], ev[5]) == cudaSuccess) out->tail_ms = ms;
+    cudaGetLastError();
+    return B200RAG_OK;
+}
+
 int b200rag_set_profiling(b200rag_shard* sp, int32_t on) {
     Shard* s = (Shard*)sp;
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
-    if (on && s->ev[0] == nullptr)
-        for (int i = 0; i < 6; ++i) B2_CUDA(cudaEventCreate(&s->ev[i]));
+    if (on && s->ev_ring[0][0] == nullptr)
+        for (int r = 0; r < kProfileRing; ++r)
+            for (int i = 0; i < 6; ++i) B2_CUDA(cudaEventCreate(&s->ev_ring[r][i]));
     s->profile = on != 0;
     s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     return B200RAG_OK;

@@ -50,7 +50,8 @@ struct DevPtr {
 };
 
 struct Workspace {
-    DevBuf q_stage;       // one H2D per batch: [q_bits | q_sp_indptr | q_sp_terms | q_sp_w | q_masks]
+                          // (the staged query blocks themselves live in Shard::slots: one H2D per batch:
+                          //  [q_bits | q_sp_indptr | q_sp_terms | q_sp_w | q_masks])
     DevPtr q_bits;        // [B, dim] u16
     DevPtr q_sp_indptr;   // [B+1] i64
     DevPtr q_sp_terms;    // u32
@@ -70,6 +71,19 @@ struct Workspace {
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
 };
+
+// A staged query batch: its device block and the host-side facts `legs`/`fuse` need.  b200rag_stage fills slot 0;
+// b200rag_stage_slot / b200rag_use_slot keep several batches resident so that searches can be enqueued back to back.
+struct QuerySlot {
+    DevBuf buf;
+    b200rag_query q{};
+    std::vector<const uint32_t*> h_masks;
+    int64_t q_terms = 0;
+    void *bits = nullptr, *ind = nullptr, *terms = nullptr, *w = nullptr, *masks = nullptr;
+    bool staged = false;
+};
+
+constexpr int kProfileRing = 64;   // legs calls whose event timings stay readable (b200rag_get_stats_step)
 
 struct Shard {
     b200rag_config cfg{};
@@ -121,7 +135,8 @@ struct Shard {
     std::map<int32_t, DevBuf> masks;
     std::map<int32_t, int64_t> mask_rows;
 
-    // staged query batch
+    // staged query batches; `q`, `h_masks`, `staged_q_terms` and ws.q_* describe the ACTIVE slot
+    std::vector<QuerySlot> slots;
     b200rag_query q{};
     bool staged = false;
     std::vector<const uint32_t*> h_masks;
@@ -131,7 +146,12 @@ struct Shard {
     Workspace ws;
     b200rag_stats stats{};
     bool profile = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // dense scan begin/end, sparse scan begin/end, legs entry, fuse end
+    // profiling events: dense scan begin/end, sparse scan begin/end, legs entry, fuse end; `ev` points at the set of the
+    // current legs call inside a ring of kProfileRing sets, so back-to-back (unsynchronised) searches keep their timings
+    cudaEvent_t ev_ring[kProfileRing][6] = {};
+    bool ev_flags[kProfileRing][4] = {};       // dense, sparse, in, out recorded
+    cudaEvent_t* ev = ev_ring[0];
+    int64_t legs_calls = 0;
     bool ev_dense = false, ev_sparse = false, ev_in = false, ev_out = false;
 
     // peer-memory exchange window (b200rag_p2p_*): [2 parities][world][slot_bytes] | [world] flags, 128 bytes apart

@@ -143,6 +143,12 @@ int b200rag_search(b200rag_shard* s, const b200rag_query* q, int64_t* out_ids_ho
  * gathered buffer is [n_shards, nlegs*batch*L + 1]; fuse then also writes the sum of the counters to
  * out_counts_dev[batch] (so out_counts_dev holds batch + 1 ints). */
 int b200rag_stage(b200rag_shard* s, const b200rag_query* q);
+/* Several staged batches at once (slot 0 is the one b200rag_stage uses): stage_slot copies a batch into its own device
+ * block and makes it the active one; use_slot re-activates an already staged batch without any copy, so a caller can
+ * keep a queue of query batches resident in HBM and enqueue legs/exchange/fuse for them back to back with no host
+ * synchronisation in between.  Staged batches are invalidated by b200rag_mask_set / b200rag_mask_drop / b200rag_clear. */
+int b200rag_stage_slot(b200rag_shard* s, const b200rag_query* q, int32_t slot);
+int b200rag_use_slot(b200rag_shard* s, int32_t slot);
 int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L);
 int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
 int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int32_t has_trailer,
@@ -190,6 +196,9 @@ typedef struct {
     float tail_ms;               /* ... from the end of the dense scan to the end of the last `fuse`               */
 } b200rag_stats;
 int b200rag_get_stats(const b200rag_shard* s, b200rag_stats* out);
+/* With profiling on: event timings of the legs call made `steps_back` calls ago (0 = the last one, < 64), for callers
+ * that enqueue many searches before synchronising; only the four *_ms fields of `out` are filled. */
+int b200rag_get_stats_step(const b200rag_shard* s, int32_t steps_back, b200rag_stats* out);
 /* Bracket the two scan kernels with CUDA events on the launching stream (bench.py's roofline figures). */
 int b200rag_set_profiling(b200rag_shard* s, int32_t on);
 
