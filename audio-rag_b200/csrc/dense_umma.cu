@@ -540,6 +540,9 @@ static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nl
         int stages = (int)((max_smem - fixed - list_bytes) / stage_bytes);
         const int max_stages = pair ? kGemmStagesPair : kGemmStages;
         if (stages > max_stages) stages = max_stages;
+        // a hybrid batch whose sparse leg runs concurrently: leave ~64 KB of the SM's shared memory to its CTAs
+        if (s->gemm_smem_reserve > 0)
+            while (stages > 2 && fixed + (size_t)stages * stage_bytes + list_bytes + s->gemm_smem_reserve > max_smem) --stages;
         const size_t smem = fixed + (size_t)stages * stage_bytes + list_bytes;
         const int grid = pair ? 2 * units2 : grid1;
         CUtensorMap map_q;

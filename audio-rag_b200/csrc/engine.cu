@@ -143,8 +143,14 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // (only with the SIMT scan, i.e. 1-2 queries: the tcgen05 path fills shared memory, nothing can co-reside with it.
     // Measured on B200: overlapped beats back-to-back at 1.25M, 10M and 12.5M rows, top-10 and top-100.)
     const bool use_gemm_path = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
-    const bool overlap = want_dense && want_sparse && s->overlap_legs && s->side_stream != nullptr && s->n_rows > 0 &&
-                         (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows) && !use_gemm_path;
+    // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
+    // nothing could co-reside.  The FILTER epilogue keeps no per-query state (96 registers); with one pipeline stage
+    // less it leaves room for a sparse CTA per SM, and the two legs overlap like in the single-query case.
+    const bool overlap_base = want_dense && want_sparse && s->overlap_legs && s->side_stream != nullptr && s->n_rows > 0 &&
+                              (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows);
+    const bool overlap_batched = overlap_base && use_gemm_path && s->overlap_gemm && s->gemm_filter && s->slack == 0 &&
+                                 s->nnz > 0 && s->staged_q_terms > 0;
+    const bool overlap = overlap_base && (!use_gemm_path || overlap_batched);
     b200rag_cand* out_dense = cands;
     b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
     if (overlap) {
@@ -165,7 +171,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             uint64_t* approx = nullptr;
             // tcgen05 path with a top-k too large for register lists: sample + filter (128 queries per pass whatever
             // the top-k).  A retry (slack widened after an ambiguous result) takes the robust list path instead.
-            const bool filtered = use_gemm && Lc > 64 && s->slack == 0 && s->gemm_filter;
+            const bool filtered = use_gemm && (Lc > 64 || overlap_batched) && s->slack == 0 && s->gemm_filter;
+            s->gemm_smem_reserve = overlap_batched ? (size_t)64 * 1024 : 0;
             if (filtered) {
                 B2_TRY(launch_dense_gemm_filtered(s, B, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(),
                                                   s->ws.lists_a.as<uint64_t>() + (size_t)B * nl_max * Lc - (size_t)B * Lc,
@@ -178,6 +185,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
                     B2_TRY(launch_merge_tree(s, B, nlists, Lc, s->ws.lists_a.as<uint64_t>(), s->ws.lists_b.as<uint64_t>(), &approx));
             }
             s->dense_stage_cap = 0;
+            s->gemm_smem_reserve = 0;
             const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
             if (approx == nullptr) {
                 B2_TRY(launch_leg_tail(s, false, B, nlists, Lc, L, s->ws.lists_a.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
@@ -315,6 +323,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_GEMM_FILTER")) s->gemm_filter = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_GEMM_PAIRS")) s->gemm_pairs = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_FUSED_TAIL")) s->fused_tail = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_OVERLAP_GEMM")) s->overlap_gemm = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }

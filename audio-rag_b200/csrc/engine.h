@@ -102,6 +102,8 @@ struct Shard {
     int sparse_bpc = 0;                   // knob: blocks per sparse-scan CTA (0 = auto)
     int sparse_threads = 128;             // knob: threads per sparse-scan CTA (128 or 256)
     bool fused_tail = true;               // knob: merge + re-score + finalize of a leg in one launch when the lists fit shared memory
+    size_t gemm_smem_reserve = 0;         // set while a hybrid batch overlaps its legs: smem the tcgen05 kernel leaves free per SM
+    int overlap_gemm = 1;                 // knob: overlap the legs of BATCHED hybrid searches too (filter epilogue + fewer stages)
     bool gemm_pairs = true;               // knob: CTA pairs (cta_group::2, 256 queries per corpus pass) when > 128 queries remain
     bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
