@@ -237,16 +237,15 @@ int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* appr
 }
 
 // ------------------------------------------------------------------------------------------------ fused leg tail
-// merge_lists (all levels) + rescore + finalize_leg in ONE launch per leg, for list sets that fit shared memory
-// (n_lists * Lc <= kTailMaxKeys).  After the scan every further launch is pure latency (4-5 launches of 5-15 us each
+// merge_lists (all levels) + rescore + finalize_leg in ONE launch per leg (n_lists * Lc <= kTailMaxKeys).  After the scan every further launch is pure latency (4-5 launches of 5-15 us each
 // plus the gaps between them), which is what caps strong scaling on small shards.
 //   1. every thread takes a strided slice of the n_lists * Lc keys and keeps its maximum; each warp sorts its 32 maxima
 //      in registers and publishes its k-th largest, k = ceil(Lc / #warps); the minimum over the warps has >= Lc keys at
 //      or above it, so only those survivors (typically a few Lc) are compacted and bitonic-sorted
 //   2. the best Lc are re-scored exactly, one warp per candidate (same canonical order as the standalone kernels)
 //   3. exact keys are sorted, thresholded, guarded and emitted exactly like finalize_leg_kernel
-constexpr int kTailMaxKeys = 8192;
-constexpr int kTailSurvivorCap = 2048;
+constexpr int kTailMaxKeys = 65536;     // the lists stay in global memory (two strided passes); only survivors go to smem
+constexpr int kTailSurvivorCap = 4096;
 
 __device__ __forceinline__ uint64_t rescore_dense_warp(const uint16_t* __restrict__ corpus, int dim,
                                                        const uint16_t* __restrict__ q_bits, int q, uint32_t row, int lane) {
@@ -484,7 +483,15 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
     p.eps_abs = eps_abs; p.eps_rel = eps_rel; p.eps_abs_q = eps_abs_q; p.has_thr = has_thr; p.thr = thr;
     p.row_base = s->cfg.row_base; p.out = out; p.ambiguous = ambiguous;
     const size_t smem = (size_t)kTailSurvivorCap * 8;
+    static bool attr = false;
+    if (!attr) {     // static + dynamic shared memory exceeds the 48 KB default of the sparse flavour
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
     if (sparse) leg_tail_kernel<true, 256><<<batch, 256, smem, s->stream>>>(p);
+    else if (Lc > 64) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);   // 32 warps re-score in parallel
     else leg_tail_kernel<false, 512><<<batch, 512, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
