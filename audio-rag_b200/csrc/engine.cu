@@ -148,8 +148,10 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // less it leaves room for a sparse CTA per SM, and the two legs overlap like in the single-query case.
     const bool overlap_base = want_dense && want_sparse && s->overlap_legs && s->side_stream != nullptr && s->n_rows > 0 &&
                               (s->overlap_max_rows <= 0 || s->n_rows <= s->overlap_max_rows);
+    // (only while the dense leg is HBM-bound, i.e. up to 128 queries per pass: measured on B200, 12.5M rows, B = 1024
+    //  top-100: overlapped 80.6 ms, back to back 77.0 ms -- a tensor-bound GEMM and the sparse scan fight for issue slots)
     const bool overlap_batched = overlap_base && use_gemm_path && s->overlap_gemm && s->gemm_filter && s->slack == 0 &&
-                                 s->nnz > 0 && s->staged_q_terms > 0;
+                                 s->nnz > 0 && s->staged_q_terms > 0 && (B <= 128 || s->overlap_gemm == 2);
     const bool overlap = overlap_base && (!use_gemm_path || overlap_batched);
     b200rag_cand* out_dense = cands;
     b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
