@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
     extern __shared__ __align__(16) uint8_t fsm[];
     const int M = n_shards * L;
     b200rag_cand* stage = reinterpret_cast<b200rag_cand*>(fsm);
-    int64_t* leg_id = reinterpret_cast<int64_t*>(stage + M);
+    int64_t* leg_id = reinterpret_cast<int64_t*>(stage + next_pow2(M));
     float* leg_score = reinterpret_cast<float*>(leg_id + 2 * L);
     double* fused = reinterpret_cast<double*>(leg_score + 2 * L);
     int64_t* fid = reinterpret_cast<int64_t*>(fused + 2 * L);
@@ -552,26 +552,61 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
         out_counts[batch] = amb;
     }
 
+    // G-way merge of a leg = sort of the gathered candidates under R5 (valid first, score desc, id asc).  Small sets
+    // (one or two shards, top-10) are ranked by counting; larger ones (8 shards x top-100 = 1600 per leg, where
+    // counting costs M^2 = 2.6 M compares and a millisecond) by a bitonic network over the 16-byte candidates.
+    const int Mp = next_pow2(M);
     for (int leg = 0; leg < nlegs; ++leg) {
         __syncthreads();
-        for (int i = threadIdx.x; i < M; i += blockDim.x) {
-            const int sh = i / L, j = i - sh * L;
-            stage[i] = gathered[(size_t)sh * shard_stride + (((size_t)leg * batch + q) * L + j)];
+        for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
+            if (i < M) {
+                const int sh = i / L, j = i - sh * L;
+                stage[i] = gathered[(size_t)sh * shard_stride + (((size_t)leg * batch + q) * L + j)];
+            } else {
+                b200rag_cand e; e.id = -1; e.score = 0.f; e.valid = 0u;
+                stage[i] = e;
+            }
         }
         __syncthreads();
-        int local = 0;
-        for (int i = threadIdx.x; i < M; i += blockDim.x) {
-            const b200rag_cand e = stage[i];
-            if (!e.valid) continue;
-            ++local;
-            int rank = 0;
-            for (int f = 0; f < M; ++f) {
-                const b200rag_cand o = stage[f];
-                if (o.valid && cand_better(o, e)) ++rank;
+        if (M <= 128) {
+            int local = 0;
+            for (int i = threadIdx.x; i < M; i += blockDim.x) {
+                const b200rag_cand e = stage[i];
+                if (!e.valid) continue;
+                ++local;
+                int rank = 0;
+                for (int f = 0; f < M; ++f) {
+                    const b200rag_cand o = stage[f];
+                    if (o.valid && cand_better(o, e)) ++rank;
+                }
+                if (rank < L) { leg_id[leg * L + rank] = e.id; leg_score[leg * L + rank] = e.score; }
             }
-            if (rank < L) { leg_id[leg * L + rank] = e.id; leg_score[leg * L + rank] = e.score; }
+            if (local) atomicAdd(&leg_n[leg], local);
+        } else {
+            for (int k = 2; k <= Mp; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const b200rag_cand a = stage[i], b = stage[ixj];
+                            // "a before b": valid before invalid, then the leg order
+                            const bool a_first = a.valid && (!b.valid || cand_better(a, b));
+                            const bool b_first = b.valid && (!a.valid || cand_better(b, a));
+                            const bool up = (i & k) == 0;           // ascending position = better first
+                            if (up ? b_first : a_first) { stage[i] = b; stage[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            int local = 0;
+            for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
+                const b200rag_cand e = stage[i];
+                if (!e.valid) continue;
+                ++local;
+                if (i < L) { leg_id[leg * L + i] = e.id; leg_score[leg * L + i] = e.score; }
+            }
+            if (local) atomicAdd(&leg_n[leg], local);
         }
-        if (local) atomicAdd(&leg_n[leg], local);
     }
     __syncthreads();
     const int nd = min(leg_n[0], L);
@@ -663,7 +698,7 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
                 int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts,
                 int64_t shard_stride_override, const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     const int nlegs = mode == B200RAG_HYBRID ? 2 : 1;
-    const size_t M = (size_t)n_shards * L;
+    const size_t M = (size_t)next_pow2(n_shards * L);
     const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
     if (smem > 200 * 1024) { set_error("fuse: n_shards * L too large"); return B200RAG_ERR_INVALID; }
     static size_t attr = 0;
