@@ -82,6 +82,8 @@ SYMBOLS = [
     ("b200rag_stage", C.c_int, [_P, C.POINTER(Query)]),
     ("b200rag_stage_slot", C.c_int, [_P, C.POINTER(Query), C.c_int32]),
     ("b200rag_use_slot", C.c_int, [_P, C.c_int32]),
+    ("b200rag_normalize_bf16_device", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("b200rag_stage_device", C.c_int, [_P, C.POINTER(Query), C.c_int32]),
     ("b200rag_legs_len", C.c_int, [C.POINTER(Query), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("b200rag_legs", C.c_int, [_P, _P, _P]),
     ("b200rag_fuse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
@@ -288,6 +290,35 @@ class Shard:
         """Copy a query batch to the device (its own block per `slot`) and make it the active one."""
         self._keep = keep
         check(self._lib.b200rag_stage_slot(self._h, C.byref(q), slot))
+
+    def normalize_bf16_device(self, x_dev, n: int, out_bits_dev):
+        """Device twin of normalize_bf16 (bit-equal): fp32 rows [n, dim] -> unit bf16 bits [n, dim], both on the GPU."""
+        check(self._lib.b200rag_normalize_bf16_device(self._h, _ptr(x_dev), n, _ptr(out_bits_dev)))
+
+    def stage_device(self, mode, top_k, batch, q_bits_dev=None, sp_indptr=None, sp_terms_dev=None, sp_weights_dev=None,
+                     mask_ids=None, score_threshold=None, rrf_k=0, slot: int = 0):
+        """Stage a batch whose vectors / sparse terms / weights already live on the GPU (device pointers or tensors);
+        `sp_indptr` (batch + 1) and `mask_ids` are small host arrays.  Returns the query struct (for legs_len)."""
+        mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        keep = []
+        if sp_indptr is not None:
+            sp_indptr = np.ascontiguousarray(sp_indptr, dtype=np.int64)
+            keep.append(sp_indptr)
+        if mask_ids is not None:
+            mask_ids = np.ascontiguousarray(mask_ids, dtype=np.int32)
+            keep.append(mask_ids)
+
+        def dp(x):
+            p = _ptr(x)
+            return None if p is None else p.value
+
+        q = Query(mode, batch, top_k, rrf_k, 0 if score_threshold is None else 1,
+                  0.0 if score_threshold is None else float(score_threshold), dp(q_bits_dev),
+                  sp_indptr.ctypes.data if sp_indptr is not None else None, dp(sp_terms_dev), dp(sp_weights_dev),
+                  mask_ids.ctypes.data if mask_ids is not None else None)
+        self._keep = keep
+        check(self._lib.b200rag_stage_device(self._h, C.byref(q), slot))
+        return q
 
     def use_slot(self, slot: int):
         """Re-activate an already staged batch (no copy, no synchronisation)."""

@@ -62,6 +62,41 @@ __global__ void offset_copy_i64_kernel(int64_t* __restrict__ dst, const int64_t*
     if (i < n) dst[i] = src[i] + offset;
 }
 
+// device twin of b200rag_normalize_bf16: one thread per row, the host routine's fp64 operations in the host's order
+__global__ void normalize_bf16_kernel(const float* __restrict__ x, int64_t n, int dim, uint16_t* __restrict__ out,
+                                      int* __restrict__ bad) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* row = x + r * (int64_t)dim;
+    double ss = 0.0;
+    bool finite = true;
+    for (int k = 0; k < dim; ++k) {
+        const double v = (double)row[k];
+        finite = finite && isfinite(v);
+        ss = __dadd_rn(ss, __dmul_rn(v, v));
+    }
+    if (!finite) { atomicExch(bad, 1); return; }
+    double nrm = sqrt(ss);
+    if (nrm == 0.0) nrm = 1.0;
+    for (int k = 0; k < dim; ++k) {
+        const float y = (float)__ddiv_rn((double)row[k], nrm);
+        uint32_t u = __float_as_uint(y);
+        u = u + 0x7FFFu + ((u >> 16) & 1u);
+        out[r * (int64_t)dim + k] = (uint16_t)(u >> 16);
+    }
+}
+
+// sparse query validation on the device: terms < vocab, strictly ascending inside each query
+__global__ void validate_sparse_query_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ terms,
+                                             int batch, uint32_t vocab, int* __restrict__ bad) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    for (int64_t i = indptr[b] + threadIdx.x; i < indptr[b + 1]; i += blockDim.x) {
+        if (terms[i] >= vocab) atomicExch(bad, 1);
+        if (i > indptr[b] && terms[i] <= terms[i - 1]) atomicExch(bad, 2);
+    }
+}
+
 static int use_device(const Shard* s) {
     B2_CUDA(cudaSetDevice(s->cfg.device));
     return B200RAG_OK;
@@ -354,6 +389,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
     for (auto& sl : s->slots) sl.buf.release();
+    s->ws.flag.release();
     s->ws.thr.release(); s->ws.lists_a.release(); s->ws.lists_b.release();
     s->ws.exact.release(); s->ws.pool.release(); s->ws.cands.release(); s->ws.out.release();
     s->ws.lists_c.release(); s->ws.lists_d.release(); s->ws.exact2.release(); s->ws.q_eps.release();
@@ -558,7 +594,28 @@ int b200rag_use_slot(b200rag_shard* sp, int32_t slot) {
     return B200RAG_OK;
 }
 
-int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) {
+static int stage_impl(b200rag_shard* sp, const b200rag_query* q, int32_t slot, bool dev);
+
+int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) { return stage_impl(sp, q, slot, false); }
+int b200rag_stage_device(b200rag_shard* sp, const b200rag_query* q, int32_t slot) { return stage_impl(sp, q, slot, true); }
+
+int b200rag_normalize_bf16_device(b200rag_shard* sp, const float* x, int64_t n, uint16_t* out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || x == nullptr || out == nullptr || n < 0) { set_error("normalize_device: bad argument"); return B200RAG_ERR_INVALID; }
+    if (n == 0) return B200RAG_OK;
+    B2_TRY(use_device(s));
+    B2_TRY(s->ws.flag.ensure(4, 0, s->stream));
+    B2_CUDA(cudaMemsetAsync(s->ws.flag.p, 0, 4, s->stream));
+    normalize_bf16_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s->stream>>>(x, n, s->dim, out, s->ws.flag.as<int>());
+    B2_CUDA(cudaGetLastError());
+    int bad = 0;
+    B2_CUDA(cudaMemcpyAsync(&bad, s->ws.flag.p, 4, cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    if (bad) { set_error("normalize: non-finite input"); return B200RAG_ERR_INVALID; }
+    return B200RAG_OK;
+}
+
+static int stage_impl(b200rag_shard* sp, const b200rag_query* q, int32_t slot, bool dev) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || q == nullptr) { set_error("stage: null argument"); return B200RAG_ERR_INVALID; }
     if (slot < 0 || slot >= 4096) { set_error("stage: slot out of range"); return B200RAG_ERR_INVALID; }
@@ -575,6 +632,7 @@ int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) 
         if (nt > 0 && (q->q_sp_terms == nullptr || q->q_sp_weights == nullptr)) { set_error("stage: sparse query terms missing"); return B200RAG_ERR_INVALID; }
         for (int b = 0; b < B; ++b) {
             if (q->q_sp_indptr[b + 1] < q->q_sp_indptr[b]) { set_error("stage: sparse query indptr not monotone"); return B200RAG_ERR_INVALID; }
+            if (dev) continue;       // terms live on the device: validated there, below
             for (int64_t i = q->q_sp_indptr[b]; i < q->q_sp_indptr[b + 1]; ++i) {
                 if (q->q_sp_terms[i] >= (uint32_t)s->vocab) { set_error("stage: sparse query index out of vocabulary range"); return B200RAG_ERR_INVALID; }
                 if (i > q->q_sp_indptr[b] && q->q_sp_terms[i] <= q->q_sp_terms[i - 1]) { set_error("stage: sparse query indices must be ascending and unique"); return B200RAG_ERR_INVALID; }
@@ -610,14 +668,16 @@ int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) 
     B2_TRY(ensure_pinned(s, total + (size_t)B * q->top_k * 16 + (size_t)(B + 1) * 4 + 1024));
     if ((size_t)slot >= s->slots.size()) s->slots.resize((size_t)slot + 1);
     QuerySlot& sl = s->slots[(size_t)slot];
+    sl.staged = false;
     B2_TRY(sl.buf.ensure(total, 0, s->stream));
     // the previous batch's H2D must have drained before the pinned block is rewritten
     B2_CUDA(cudaStreamSynchronize(s->stream));
     uint8_t* h = (uint8_t*)s->h_pinned;
-    if (need_dense) memcpy(h + o_bits, q->q_dense_bits, (size_t)B * s->dim * 2);
+    uint8_t* d = sl.buf.as<uint8_t>();
+    if (need_dense && !dev) memcpy(h + o_bits, q->q_dense_bits, (size_t)B * s->dim * 2);
     if (need_sparse) {
         memcpy(h + o_ind, q->q_sp_indptr, (size_t)(B + 1) * 8);
-        if (nt > 0) {
+        if (nt > 0 && !dev) {
             memcpy(h + o_terms, q->q_sp_terms, (size_t)nt * 4);
             memcpy(h + o_w, q->q_sp_weights, (size_t)nt * 4);
         }
@@ -626,8 +686,28 @@ int b200rag_stage_slot(b200rag_shard* sp, const b200rag_query* q, int32_t slot) 
     }
     if (any_mask) memcpy(h + o_masks, s->h_masks.data(), (size_t)B * 8);
     else memset(h + o_masks, 0, (size_t)B * 8);
-    B2_CUDA(cudaMemcpyAsync(sl.buf.p, h, total, cudaMemcpyHostToDevice, s->stream));
-    uint8_t* d = sl.buf.as<uint8_t>();
+    if (!dev) {
+        B2_CUDA(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        // host part: indptr + mask pointers; device part: vectors, terms and weights, copied device to device
+        B2_CUDA(cudaMemcpyAsync(d + o_ind, h + o_ind, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        B2_CUDA(cudaMemcpyAsync(d + o_masks, h + o_masks, (size_t)B * 8, cudaMemcpyHostToDevice, s->stream));
+        if (need_dense) B2_CUDA(cudaMemcpyAsync(d + o_bits, q->q_dense_bits, (size_t)B * s->dim * 2, cudaMemcpyDeviceToDevice, s->stream));
+        if (need_sparse && nt > 0) {
+            B2_CUDA(cudaMemcpyAsync(d + o_terms, q->q_sp_terms, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s->stream));
+            B2_CUDA(cudaMemcpyAsync(d + o_w, q->q_sp_weights, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s->stream));
+            B2_TRY(s->ws.flag.ensure(4, 0, s->stream));
+            B2_CUDA(cudaMemsetAsync(s->ws.flag.p, 0, 4, s->stream));
+            validate_sparse_query_kernel<<<B, 128, 0, s->stream>>>((const int64_t*)(d + o_ind), (const uint32_t*)(d + o_terms), B,
+                                                                   (uint32_t)s->vocab, s->ws.flag.as<int>());
+            B2_CUDA(cudaGetLastError());
+            int bad = 0;
+            B2_CUDA(cudaMemcpyAsync(&bad, s->ws.flag.p, 4, cudaMemcpyDeviceToHost, s->stream));
+            B2_CUDA(cudaStreamSynchronize(s->stream));
+            if (bad == 1) { set_error("stage: sparse query index out of vocabulary range"); return B200RAG_ERR_INVALID; }
+            if (bad == 2) { set_error("stage: sparse query indices must be ascending and unique"); return B200RAG_ERR_INVALID; }
+        }
+    }
     sl.bits = d + o_bits;
     sl.ind = d + o_ind;
     sl.terms = d + o_terms;

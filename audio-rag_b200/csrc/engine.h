@@ -66,6 +66,7 @@ struct Workspace {
     DevBuf lists_d;
     DevBuf exact2;
     DevBuf q_eps;         // [B] f32 absolute error bound of the sparse scan's approximate scores | [B] i32 grid-wide thresholds
+    DevBuf flag;          // 4-byte device flag for validation kernels
     DevBuf xpeers_dev;    // [world] void*: exchange windows of all ranks (peer pointers)
     DevBuf pool;          // filter path of the tcgen05 kernel: [B, cap] u64 keys | [B] i32 counters
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)

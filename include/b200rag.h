@@ -149,6 +149,14 @@ int b200rag_stage(b200rag_shard* s, const b200rag_query* q);
  * synchronisation in between.  Staged batches are invalidated by b200rag_mask_set / b200rag_mask_drop / b200rag_clear. */
 int b200rag_stage_slot(b200rag_shard* s, const b200rag_query* q, int32_t slot);
 int b200rag_use_slot(b200rag_shard* s, int32_t slot);
+/* Device-resident queries (the embedder's outputs never leave the GPU; embeddings/bge.py:137-157 moves them
+ * to Python lists today).  normalize_bf16_device is the device twin of b200rag_normalize_bf16 (bit-equal output: the
+ * same fp64 operations in the same order, one thread per row).  stage_device is b200rag_stage_slot with q_dense_bits,
+ * q_sp_terms and q_sp_weights pointing to DEVICE memory (device-to-device copies on the shard's stream);
+ * q_sp_indptr and mask_ids stay host arrays (batch + 1 small integers the caller knows anyway).  The sparse terms are
+ * validated on the device (in range, ascending and unique per query). */
+int b200rag_normalize_bf16_device(b200rag_shard* s, const float* x_dev, int64_t n, uint16_t* out_bits_dev);
+int b200rag_stage_device(b200rag_shard* s, const b200rag_query* q, int32_t slot);
 int b200rag_legs_len(const b200rag_query* q, int32_t* nlegs, int32_t* L);
 int b200rag_legs(b200rag_shard* s, void* cands_dev, int32_t* ambiguous_dev);
 int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, int32_t has_trailer,

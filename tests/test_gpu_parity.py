@@ -418,3 +418,51 @@ def test_sparse_fixed_point_edge_cases(gpu, R):
     ei, es = oracle_search(c, "hybrid", qb[0], cases[1][0], cases[1][1], None, 10)
     assert_result_equal(ids[0], scores[0], int(counts[0]), ei, es, ctx=f"R={R} hybrid")
     sh.close()
+
+
+def test_device_resident_queries(gpu):
+    """SURVEY 8f: queries that never leave the GPU.  normalize_bf16_device is bit-equal to the host routine;
+    stage_device + legs + fuse returns exactly what the host-buffer search returns; bad device-side sparse input is
+    refused; several staged slots can be replayed in any order."""
+    import torch
+    from b200rag import Shard, normalize_bf16
+    from b200rag._ffi import B200RagError
+    c = Corpus(9_000, dim=1024, vocab=30_011)
+    sh = _shard_from(c, gpu, docs_per_block=2048)
+    dev = torch.device("cuda", gpu)
+    sh.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    B, k = 5, 10
+    qf, ip, tt, ww = c.queries(B)
+    x = torch.from_numpy(np.ascontiguousarray(qf, dtype=np.float32)).to(dev)
+    bits = torch.empty((B, 1024), dtype=torch.int16, device=dev)
+    sh.normalize_bf16_device(x, B, bits)
+    qb = normalize_bf16(qf)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint16), qb)
+    t_dev = torch.from_numpy(tt.astype(np.int32)).to(dev)
+    w_dev = torch.from_numpy(ww).to(dev)
+    # (slot 0 is the one the host-buffer search below re-stages: the device batches live in slots 1..3)
+    for slot, mode in enumerate(("hybrid", "dense", "sparse"), start=1):
+        sh.stage_device(mode, k, B, bits if mode != "sparse" else None, ip if mode != "dense" else None,
+                        t_dev if mode != "dense" else None, w_dev if mode != "dense" else None, slot=slot)
+    for slot, mode in reversed(list(enumerate(("hybrid", "dense", "sparse"), start=1))):
+        sh.use_slot(slot)
+        nl = 2 if mode == "hybrid" else 1
+        L = 2 * k if mode == "hybrid" else k
+        cands = torch.zeros((nl * B * L + 1, 2), dtype=torch.int64, device=dev)
+        oi = torch.empty((B, k), dtype=torch.int64, device=dev)
+        osc = torch.empty((B, k), dtype=torch.float64, device=dev)
+        oc = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        sh.legs(cands, cands[-1])
+        sh.fuse(cands, 1, oi, osc, oc, has_trailer=True)
+        sh.sync()
+        ids, scores, counts = sh.search(mode, k, qb, ip, tt, ww)     # host-buffer path (re-stages slot 0)
+        assert np.array_equal(oi.cpu().numpy(), ids) and np.array_equal(osc.cpu().numpy(), scores)
+        assert np.array_equal(oc.cpu().numpy()[:B], counts) and oc.cpu().numpy()[B] == 0
+    bad = t_dev.clone()
+    bad[1] = bad[0]                                                    # duplicate index inside query 0
+    with pytest.raises(B200RagError):
+        sh.stage_device("sparse", k, B, None, ip, bad, w_dev)
+    x[0, 3] = float("nan")
+    with pytest.raises(B200RagError):
+        sh.normalize_bf16_device(x, B, bits)
+    sh.close()
