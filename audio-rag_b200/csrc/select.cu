@@ -504,6 +504,17 @@ __device__ __forceinline__ bool cand_better(const b200rag_cand& f, const b200rag
     return fo > eo || (fo == eo && f.id < e.id);
 }
 
+// Gathered candidates may have been written by PEER GPUs (exchange windows) moments ago: read them with ld.global.cg
+// (L2, which is coherent with NVLink writes) -- never through the non-coherent / L1 path a const __restrict__ pointer
+// would otherwise be allowed to take.
+__device__ __forceinline__ b200rag_cand ld_cand_cg(const b200rag_cand* p) {
+    static_assert(sizeof(b200rag_cand) == 16, "candidate is one 16-byte word pair");
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+    b200rag_cand c;
+    memcpy(&c, &v, 16);
+    return c;
+}
+
 // smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
 __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
                                                    int64_t shard_stride, int has_trailer, int nlegs, int batch,
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
     if (has_trailer && q == 0 && threadIdx.x == 0) {
         int amb = 0;
         for (int sh = 0; sh < n_shards; ++sh)
-            amb += (int)(gathered[(size_t)sh * shard_stride + (size_t)nlegs * batch * L].id & 0xFFFFFFFFll);
+            amb += (int)(ld_cand_cg(gathered + (size_t)sh * shard_stride + (size_t)nlegs * batch * L).id & 0xFFFFFFFFll);
         out_counts[batch] = amb;
     }
 
@@ -561,7 +572,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restric
         for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
             if (i < M) {
                 const int sh = i / L, j = i - sh * L;
-                stage[i] = gathered[(size_t)sh * shard_stride + (((size_t)leg * batch + q) * L + j)];
+                stage[i] = ld_cand_cg(gathered + (size_t)sh * shard_stride + (((size_t)leg * batch + q) * L + j));
             } else {
                 b200rag_cand e; e.id = -1; e.score = 0.f; e.valid = 0u;
                 stage[i] = e;

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) sparse_scan_kernel(cons
                 }
             }
         }
-        if (tid == 0) tau_s = p.gthr != nullptr ? p.gthr[q] : kNone;
+        if (tid == 0) tau_s = p.gthr != nullptr ? *reinterpret_cast<volatile int*>(&p.gthr[q]) : kNone;   // fresh every block
         __syncthreads();
         if (!any) continue;   // block shares no term with the query: accumulators are still zero (uniform branch)
         if (tau_s > (int)0x80808080 && tau_s > tau) tau = tau_s;   // (memset pattern 0x80808080 == none yet)
