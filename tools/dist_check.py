@@ -45,6 +45,30 @@ def main():
             ref = t.clone()
             dist.broadcast(ref, src=0)
             bad += 0 if torch.equal(t, ref) else 1
+    # ---- stress: 120 different queries staged in slots, enqueued back to back with NO host synchronisation (the bench's
+    # timed loop); every step's fused output is copied aside on the stream and checked afterwards.  A stale read of a
+    # peer-written exchange slot or a broken epoch/parity protocol shows up here.
+    nst, k = 120, 10
+    qf2, ip2, tt2, ww2 = c.queries(nst, qid_start=100)
+    qb2 = normalize_bf16(qf2)
+    for i in range(nst):
+        ss.stage("hybrid", k, qb2[i:i + 1], ip2[i:i + 2] - ip2[i], tt2[ip2[i]:ip2[i + 1]], ww2[ip2[i]:ip2[i + 1]], slot=i)
+    keep = None
+    for i in range(nst):
+        ss.use_slot(i)
+        b = ss.run_staged()
+        if keep is None:
+            keep = torch.empty((nst,) + tuple(b["out"].shape), dtype=b["out"].dtype, device=dev)
+        keep[i].copy_(b["out"], non_blocking=True)
+    torch.cuda.synchronize(dev)
+    hk = keep.cpu().numpy()
+    for i in range(nst):
+        ids_i = hk[i, :k]
+        sc_i = hk[i, k:2 * k].view(np.float64)
+        cnt_i = hk[i, 2 * k:].view(np.int32)
+        ei, es = oracle_search(c, "hybrid", qb2[i], tt2[ip2[i]:ip2[i + 1]], ww2[ip2[i]:ip2[i + 1]], None, k)
+        ok = cnt_i[0] == len(ei) and np.array_equal(ids_i[:len(ei)], ei) and np.array_equal(sc_i[:len(ei)], es) and cnt_i[1] == 0
+        bad += 0 if ok else 1
     tot = torch.tensor([bad], device=dev)
     dist.all_reduce(tot)
     if rank == 0:
