@@ -26,6 +26,26 @@ class OracleShard:
     def close(self):
         pass
 
+    # persistence twin of b200rag_save / b200rag_load (same refusal rules: empty shard, matching geometry)
+    def save(self, path):
+        ix = self.index
+        np.savez(path + ".npz", dim=self.dim, vocab=self.vocab, bits=ix.bits, indptr=ix.indptr, terms=ix.terms,
+                 weights=ix.weights)
+        import os
+        os.replace(path + ".npz", path)
+
+    def load(self, path):
+        if self.index.n:
+            raise RuntimeError("load: the shard must be empty")
+        try:
+            z = np.load(path, allow_pickle=False)
+            if int(z["dim"]) != self.dim or int(z["vocab"]) != self.vocab:
+                raise RuntimeError("load: file was written for another dim/vocab")
+        except (ValueError, OSError, KeyError) as e:
+            raise RuntimeError(f"load: not a shard file ({e})")
+        ix = self.index
+        ix.bits, ix.indptr, ix.terms, ix.weights = z["bits"], z["indptr"], z["terms"], z["weights"]
+
     @property
     def count(self):
         return self.index.n

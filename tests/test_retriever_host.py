@@ -139,6 +139,55 @@ def test_default_collection_threshold_and_batch():
     assert "poison" not in ours.search(qs[0])[0].chunk.metadata
 
 
+def test_save_load_host_logic(tmp_path):
+    """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
+    retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
+    mismatching or corrupt directories."""
+    from audio_rag.core import RetrievalError
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever
+    A, E, S = _types()
+    ref, ours = _pair(top_k=5)
+    sets = {"tenant_a": make_chunks(80, 11, "A", A, E, S), "tenant_b": make_chunks(60, 12, "B", A, E, S),
+            "legacy": make_chunks(40, 13, "L", A, E, S, sparse=False), "dropped": make_chunks(30, 15, "X", A, E, S)}
+    for name, (ch, em) in sets.items():
+        ref.add(ch, em, name)
+        ours.add(ch, em, name)
+    ref.delete_collection("dropped")
+    ours.delete_collection("dropped")
+    d = str(tmp_path / "saved")
+    ours.save(d)
+    manifest = json.load(open(os.path.join(d, "manifest.json")))
+    assert manifest["rows"] == 210 and sum(manifest["alive"]) == 180
+    assert manifest["collections"]["legacy"]["hybrid"] is False and manifest["collections"]["dropped"]["exists"] is False
+    assert sum(1 for _ in open(os.path.join(d, "payloads.jsonl"), encoding="utf-8")) == 210
+
+    def fresh(dim=DIM):
+        r = B200Retriever(RetrievalConfig(top_k=5), embedding_dim=dim)
+        r._shard = OracleShard(dim=dim)
+        return r
+
+    back = fresh()
+    back.load(d)
+    qs = make_queries(4, 21, 80, 11, E, S)
+    _compare_all(ref, back, qs, ["tenant_a", "tenant_b", "legacy"], search_type="hybrid")
+    _compare_all(ref, back, qs[:2], ["tenant_a"], search_type="dense", filter_metadata={"lang": "en"})
+    assert back.count("tenant_a") == 80 and not back.collection_exists("dropped")
+    ch, em = make_chunks(10, 16, "A3", A, E, S)
+    ref.add(ch, em, "tenant_a")
+    back.add(ch, em, "tenant_a")
+    _compare_all(ref, back, qs[:2], ["tenant_a"], search_type="hybrid")
+    # refusals: non-empty target, other geometry, damaged manifest / payload file
+    with pytest.raises(RetrievalError):
+        back.load(d)
+    with pytest.raises(RetrievalError):
+        fresh(dim=DIM * 2).load(d)
+    lines = open(os.path.join(d, "payloads.jsonl"), encoding="utf-8").readlines()
+    open(os.path.join(d, "payloads.jsonl"), "w", encoding="utf-8").writelines(lines[:-3])
+    with pytest.raises(RetrievalError):
+        fresh().load(d)
+
+
 def test_golden_fixture_is_current():
     """tests/golden/retrieval_golden.json was produced by make_golden.py from the reference plugin + test double."""
     import make_golden
