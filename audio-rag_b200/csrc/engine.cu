@@ -172,11 +172,10 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     const bool want_sparse = q.mode != B200RAG_DENSE;
     if (want_sparse && s->built_rows != s->n_rows) B2_TRY(build_inverted(s));
 
-    // Hybrid: the sparse leg (scan + merges + exact re-score) runs on the side stream while the dense scan streams the
-    // corpus.  The dense scan is issued FIRST so its persistent CTAs (1 per SM, ring capped at 5 stages = 168 KB) are
-    // resident, and one 46 KB sparse CTA per SM co-resides with them.
-    // (only with the SIMT scan, i.e. 1-2 queries: the tcgen05 path fills shared memory, nothing can co-reside with it.
-    // Measured on B200: overlapped beats back-to-back at 1.25M, 10M and 12.5M rows, top-10 and top-100.)
+    // Hybrid: the sparse leg (scan + fused tail) runs on the side stream while the dense scan streams the corpus.
+    // The dense scan is issued FIRST so its persistent CTAs (1 per SM, 3-stage ring = 105 KB) are resident, and the
+    // sparse CTAs (39 KB, 64 registers) co-reside with them.  Measured on B200: overlapped beats back-to-back at
+    // 1.25M, 10M and 12.5M rows, top-10 and top-100 (10M: 3.26 vs 3.36 ms per search).
     const bool use_gemm_path = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
     // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
     // nothing could co-reside.  The FILTER epilogue keeps no per-query state (96 registers); with one pipeline stage

@@ -335,11 +335,17 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
 #pragma unroll
     for (int w = 1; w < NW; ++w) tau = wk_s[w] < tau ? wk_s[w] : tau;
     if (tau == 0) tau = 1;                 // fewer than Lc real keys: keep every non-empty slot
-    for (int i = tid; i < total; i += NT) {
-        const uint64_t k = src[i];
-        if (k >= tau) {
-            const int pos = atomicAdd(&cnt_s, 1);
-            if (pos < kTailSurvivorCap) tkeys[pos] = k;
+    for (int i0 = warp * 32; i0 < total; i0 += NT) {      // warp-uniform trip count: one shared atomic per warp and round
+        const int i = i0 + lane;
+        const uint64_t k = i < total ? src[i] : 0ull;
+        const bool take = k >= tau;
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m != 0) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cnt_s, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (take && pos < kTailSurvivorCap) tkeys[pos] = k;
         }
     }
     __syncthreads();
@@ -516,7 +522,7 @@ __device__ __forceinline__ b200rag_cand ld_cand_cg(const b200rag_cand* p) {
 }
 
 // smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
-__global__ void __launch_bounds__(256) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
+__global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
                                                    int64_t shard_stride, int has_trailer, int nlegs, int batch,
                                                    int L, int top_k, int rrf_k,
                                                    int64_t* __restrict__ out_ids, double* __restrict__ out_scores,
@@ -719,7 +725,8 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
     }
     const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
-    fuse_kernel<<<batch, 256, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
+    const int fuse_threads = (size_t)n_shards * L > 512 ? 1024 : 256;     // the bitonic merge of large sets wants more lanes
+    fuse_kernel<<<batch, fuse_threads, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
                                                  rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
