@@ -342,8 +342,6 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
     const size_t max_smem = 227 * 1024;
     const size_t merge_bytes = sh ? 0 : (size_t)next_pow2(kScanConsumerWarps * Lc) * 8;
 
-    const uint64_t* thr_base = s->ws.thr.as<uint64_t>();
-    (void)thr_base;
     s->stats.dense_path = 1;
     s->stats.dense_passes = 0;
 

@@ -7,19 +7,20 @@
 // GEMM shape per CTA tile:  D[128 queries x 256 corpus rows] (fp32, TMEM) = Q[128 x K] * C[256 x K]^T,
 // both operands bf16 K-major in shared memory with the 128-byte swizzle, K = dim stepped 64 elements per
 // pipeline stage (16 KB of queries + 32 KB of corpus rows per stage, 4 stages), 4 x tcgen05.mma (K = 16) per stage.
+// With more than 128 queries in a pass the kernel runs as CTA PAIRS (cluster of 2, tcgen05.mma.cta_group::2):
+// M = 256 queries, each CTA stages its own 128 queries and half of the corpus tile (32 KB per stage, 6 stages).
 // Queries are the M dimension on purpose: TMEM lane i then holds query i, so ONE epilogue thread owns ONE query and
-// keeps that query's running top-Lc threshold in a register: the common case per score is one FSETP.  Survivors are
-// inserted into the query's sorted list in shared memory by the whole warp (ballot over the 32 queries of the warp,
-// then a cooperative shift), so an insert costs O(Lc/32) steps, not O(Lc); thresholds are shared grid-wide through a
-// monotone atomicMax like in the SIMT scan.  DRAM sees contiguous reads: each 256-row tile (512 KB) is prefetched into
-// L2 as one bulk region two tiles ahead, the 128-byte-wide tensor loads then hit L2.
+// keeps that query's running threshold in a register: the common case per score is one FSETP.  Three epilogues:
+// a sorted candidate list in registers (top-k up to 64), replace-min lists in shared memory (retry path), and a
+// stateless FILTER against a fixed threshold from a 1/16 sample pass (any top-k, 128-256 queries per pass).
+// Thresholds are shared grid-wide through a monotone atomicMax like in the SIMT scan.
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over 256-row corpus tiles):
 //   warp 0  TMA producer   (one lane): cp.async.bulk.tensor.2d of the query k-block and the corpus k-block
-//   warp 1  MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit -> smem-empty / tmem-full
+//   warp 1  MMA issuer     (one lane, leader CTA of a pair): tcgen05.mma, tcgen05.commit -> smem-empty / tmem-full
 //   warp 2  TMEM allocator (512 columns = two 256-column accumulator buffers, so the epilogue of tile i overlaps
 //                           the MMAs of tile i+1)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, compare, insert
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, compare, insert / append
 //
 // Roofline: HBM for <= ~200 queries per pass (intensity = B flop/byte), tensor pipe above.
 // Algorithmic bytes per launch = n_rows * dim * 2.
@@ -152,12 +153,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// contiguous L2 prefetch (bulk, 1-D): lets DRAM stream whole 2 KB rows while the tensor loads below pick 128-byte
-// k-slices of 256 different rows per stage
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 
 // Candidate lists in shared memory, one per query: an UNSORTED set of the Lc best keys seen so far plus, in the
 // owning lane's registers, the fill count and the position/value of the current minimum (= the running threshold).
