@@ -296,14 +296,44 @@ class B200Retriever(BaseRetriever):
         except Exception as e:
             raise RetrievalError(f"Search failed: {e}")
 
-    def _execute(self, embeddings, plans) -> list[list[RetrievalResult]]:
+    def search_batch_arrays(self, query_embeddings: list[EmbeddingResult], top_k: int | None = None,
+                            collection_name: str | list[str] | None = None, filter_metadata: dict | None = None,
+                            search_type: str | None = None) -> dict:
+        """Additive (the reranker hand-off, reranking/bge.py:86-147, pipeline/query.py:145-160):
+        the same search as ``search_batch`` without building ``RetrievalResult``/``AudioChunk`` objects per hit.
+        Returns ``{"ids": int64 [B, k] (-1 padded), "scores": float64 [B, k], "counts": int32 [B], "texts": list of B
+        lists of chunk texts, "sources": list of B collection names}`` -- what a cross-encoder needs to build its
+        (query, passage) pairs in one go; ``materialise(b, j)`` turns any hit into the usual ``RetrievalResult``."""
+        names = collection_name if isinstance(collection_name, (list, tuple)) else [collection_name] * len(query_embeddings)
+        if len(names) != len(query_embeddings):
+            raise RetrievalError("search_batch_arrays: one collection name per query expected")
+        plans = [self._plan_search(q, top_k, n, filter_metadata, search_type) for q, n in zip(query_embeddings, names)]
+        k = plans[0]["top_k"] if plans else 0
+        B = len(plans)
+        ids = np.full((B, k), -1, dtype=np.int64)
+        scores = np.zeros((B, k), dtype=np.float64)
+        counts = np.zeros(B, dtype=np.int32)
+        try:
+            raw = self._execute(query_embeddings, plans, raw=True)
+        except Exception as e:
+            raise RetrievalError(f"Search failed: {e}")
+        texts = []
+        for b, (i, s, c) in enumerate(raw):
+            ids[b, :c], scores[b, :c], counts[b] = i[:c], s[:c], c
+            texts.append([self._payloads[int(r) - self._row_base].get("text", "") for r in i[:c]])
+        out = {"ids": ids, "scores": scores, "counts": counts, "texts": texts,
+               "sources": [p["collection"] for p in plans]}
+        out["materialise"] = lambda b, j: self._materialise(ids[b, j:j + 1], scores[b, j:j + 1], 1, out["sources"][b])[0]
+        return out
+
+    def _execute(self, embeddings, plans, raw: bool = False) -> list:
         results: list = [None] * len(plans)
         groups: dict = {}
         for i, p in enumerate(plans):
             if self._coll_rows.get(p["collection"], 0) == 0:
                 # the engine is still required to exist: a missing GPU/library must not look like "no results"
                 self._get_shard()
-                results[i] = []
+                results[i] = (np.zeros(0, np.int64), np.zeros(0, np.float64), 0) if raw else []
                 continue
             groups.setdefault((p["mode"], p["top_k"], p["score_threshold"]), []).append(i)
         for (mode, k, thr), idxs in groups.items():
@@ -314,7 +344,8 @@ class B200Retriever(BaseRetriever):
                                                mask_ids=mask_ids if (mask_ids >= 0).any() else None,
                                                score_threshold=thr, rrf_k=self._rrf_k)
             for j, i in enumerate(idxs):
-                results[i] = self._materialise(ids[j], scores[j], counts[j], plans[i]["collection"])
+                results[i] = (ids[j], scores[j], int(counts[j])) if raw else \
+                    self._materialise(ids[j], scores[j], counts[j], plans[i]["collection"])
         return results
 
     # ------------------------------------------------------------------ admin (qdrant.py:354-381)

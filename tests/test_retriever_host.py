@@ -139,6 +139,28 @@ def test_default_collection_threshold_and_batch():
     assert "poison" not in ours.search(qs[0])[0].chunk.metadata
 
 
+def test_search_batch_arrays_matches_search_batch():
+    """The reranker hand-off (arrays + texts, no per-hit objects) returns exactly the hits of search_batch."""
+    A, E, S = _types()
+    _, ours = _pair(top_k=7)
+    for name, seed in (("t1", 61), ("t2", 62)):
+        ch, em = make_chunks(70, seed, name.upper(), A, E, S)
+        ours.add(ch, em, name)
+    qs = make_queries(5, 63, 70, 61, E, S)
+    names = ["t1", "t2", "t1", "nope", "t2"]
+    objs = ours.search_batch(qs, top_k=7, collection_name=names, search_type="hybrid")
+    arr = ours.search_batch_arrays(qs, top_k=7, collection_name=names, search_type="hybrid")
+    assert arr["ids"].shape == (5, 7) and arr["sources"] == names
+    for b, hits in enumerate(objs):
+        assert arr["counts"][b] == len(hits)
+        assert arr["texts"][b] == [h.chunk.text for h in hits]
+        assert [float(x) for x in arr["scores"][b, :len(hits)]] == [h.score for h in hits]
+        if hits:
+            m = arr["materialise"](b, 0)
+            assert m.chunk.text == hits[0].chunk.text and m.score == hits[0].score and m.source == names[b]
+    assert arr["counts"][3] == 0 and (arr["ids"][3] == -1).all()
+
+
 def test_save_load_host_logic(tmp_path):
     """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
     retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
