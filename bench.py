@@ -259,12 +259,12 @@ def run_b200(a):
         f, ip, tt, ww = step_arrays(i)
         ss.stage(a.mode, a.top_k, normalize_bf16(f), ip, tt, ww, slot=i)
     barrier()
+    if sampler:
+        sampler.start()          # nvidia-smi needs ~0.1 s to deliver its first sample: start it before the warm-up steps
     for i in range(W):
         ss.use_slot(i)
         b = ss.run_staged()
     barrier()
-    if sampler:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
