@@ -312,13 +312,12 @@ static int launch_one(Shard* s, const DenseScanParams& p, int grid, size_t smem)
     auto kern = dense_scan_kernel<NCH, NQ, SH>;
     // attributes are set once per instantiation (and again only if a larger footprint is needed): two driver calls
     // fewer between the start of a search and its first kernel
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, smem)) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // keep the SM's shared-memory carve-out at its maximum: the ring only needs ~105 KB, and the sparse leg's CTAs
     // (side stream) are meant to co-reside in what is left
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_smem = smem;
     }
     kern<<<grid, kScanThreads, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());

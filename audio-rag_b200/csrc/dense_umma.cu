@@ -474,11 +474,9 @@ template <int LREG, int CG>
 static int launch_gemm_t(Shard* s, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmParams& p, int grid,
                          size_t smem) {
     auto kern = dense_gemm_kernel<LREG, CG>;
-    static bool attr = false;
-    if (!attr) {
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, 227 * 1024))
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -649,11 +647,9 @@ int launch_dense_gemm_filtered(Shard* s, int batch, int Lc, uint64_t* scratch_a,
     B2_TRY(gemm_passes(s, batch, Lc, nullptr, nullptr, nullptr, 1, pool, pool_cnt, cap));
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[1], s->stream)); s->ev_dense = true; }
     // 4. best Lc of each pool
-    static bool attr = false;
-    if (!attr) {
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, 8192 * 8))
         B2_CUDA(cudaFuncSetAttribute(pool_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-        attr = true;
-    }
     const int npow2_max = next_pow2(cap > Lc ? cap : Lc);
     pool_select_kernel<<<batch, 512, (size_t)npow2_max * 8, s->stream>>>(pool, pool_cnt, cap, s->ws.thr.as<uint64_t>(), Lc,
                                                                         approx, ambiguous);

@@ -35,6 +35,20 @@ struct DevBuf {
     T* as() const { return (T*)p; }
 };
 
+// Kernel function attributes (dynamic shared memory limit, carve-out) are per DEVICE: launchers cache what they set in
+// a table indexed by the device ordinal, so a process that owns shards on several GPUs configures each of them.
+constexpr int kMaxDevices = 64;
+struct AttrCache {
+    size_t smem[kMaxDevices] = {};
+    // true when `bytes` exceeds what was configured on `device` so far (and records it)
+    bool raise(int device, size_t bytes) {
+        if (device < 0 || device >= kMaxDevices) return true;
+        if (bytes <= smem[device]) return false;
+        smem[device] = bytes;
+        return true;
+    }
+};
+
 constexpr int kMaxBatchMasks = 4096;
 constexpr int kScanConsumerWarps = 8;
 constexpr int kScanTileRows = 16;

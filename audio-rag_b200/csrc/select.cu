@@ -29,12 +29,10 @@ __global__ void __launch_bounds__(512) merge_lists_kernel(const uint64_t* __rest
 }
 
 int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uint64_t* b, uint64_t** result) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, kMergeMaxKeys * 8))
         B2_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kMergeMaxKeys * 8));
-        attr_set = true;
-    }
     // Many small groups per level instead of one big sort: a bitonic network over n keys costs
     // ~log2(n)^2/2 barrier-separated stages, so groups are kept at <= kMergeGroupKeys keys and the tree
     // gets an extra (cheap, parallel) level instead.
@@ -489,12 +487,11 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
     p.eps_abs = eps_abs; p.eps_rel = eps_rel; p.eps_abs_q = eps_abs_q; p.has_thr = has_thr; p.thr = thr;
     p.row_base = s->cfg.row_base; p.out = out; p.ambiguous = ambiguous;
     const size_t smem = (size_t)kTailSurvivorCap * 8;
-    static bool attr = false;
-    if (!attr) {     // static + dynamic shared memory exceeds the 48 KB default of the sparse flavour
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, smem)) {     // static + dynamic shared memory exceeds the 48 KB default of the sparse flavour
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     if (sparse) leg_tail_kernel<true, 256><<<batch, 256, smem, s->stream>>>(p);
     else if (Lc > 64) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);   // 32 warps re-score in parallel
@@ -718,11 +715,9 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
     const size_t M = (size_t)next_pow2(n_shards * L);
     const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
     if (smem > 200 * 1024) { set_error("fuse: n_shards * L too large"); return B200RAG_ERR_INVALID; }
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    static AttrCache attr;
+    if (smem > 48 * 1024 && attr.raise(s->cfg.device, smem))
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
     const int fuse_threads = (size_t)n_shards * L > 512 ? 1024 : 256;     // the bitonic merge of large sets wants more lanes

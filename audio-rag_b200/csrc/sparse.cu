@@ -407,12 +407,10 @@ template <int NT, int EPT, int U>
 static int launch_scan_tu(Shard* s, const SparseScanParams& p, int batch) {
     const size_t smem = (size_t)EPT * NT * 4 + (size_t)p.sel_cap * 8 + (size_t)NT * 16 + 16 + (size_t)EPT * NT / 8;
     auto kern = p.masks != nullptr ? sparse_scan_kernel<NT, EPT, U, true> : sparse_scan_kernel<NT, EPT, U, false>;
-    static size_t attr_smem[2] = {0, 0};      // per instantiation and mask flavour
-    size_t& done = attr_smem[p.masks != nullptr ? 1 : 0];
-    if (smem > done) {
+    static AttrCache attr[2];                  // per instantiation and mask flavour
+    if (attr[p.masks != nullptr ? 1 : 0].raise(s->cfg.device, smem)) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        done = smem;
     }
     dim3 grid((unsigned)batch, (unsigned)p.n_groups);
     kern<<<grid, NT, smem, s->stream>>>(p);
