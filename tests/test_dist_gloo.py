@@ -34,8 +34,13 @@ class CpuShardDouble:
         return Shard.make_query(self, mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids,
                                 score_threshold, rrf_k)
 
-    def stage(self, q, keep=None):
+    def stage(self, q, keep=None, slot=0):
+        self._slots = getattr(self, "_slots", {})
+        self._slots[slot] = self._pending
         self._staged = self._pending
+
+    def use_slot(self, slot):
+        self._staged = self._slots[slot]
 
     def set_slack(self, s):
         self.slack_calls.append(s)
@@ -121,6 +126,17 @@ def _worker(rank, world, port, q):
             gathered = [None] * world
             dist.all_gather_object(gathered, ids.tolist())
             assert all(g == gathered[0] for g in gathered)
+        # a queue of staged batches replayed out of order (the bench's pre-staged slots): stage 3 single queries,
+        # run them 2, 0, 1 and compare with the oracle
+        k = 5
+        for i in range(3):
+            ss.stage("hybrid", k, qb[i:i + 1], ip[i:i + 2] - ip[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]], slot=i)
+        for i in (2, 0, 1):
+            ss.use_slot(i)
+            ids, sc, cnt, amb = ss.fetch(ss.run_staged())
+            ei, es = oracle_search(c, "hybrid", qb[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]], None, k)
+            assert amb == 0 and cnt[0] == len(ei) and np.array_equal(ids[0, :cnt[0]], ei) and np.array_equal(sc[0, :cnt[0]], es)
+        assert not ss.p2p            # CPU doubles never take the peer-memory path
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
