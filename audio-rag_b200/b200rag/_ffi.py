@@ -94,6 +94,7 @@ SYMBOLS = [
     ("b200rag_p2p_exchange", C.c_int, [_P, _P, C.c_int64]),
     ("b200rag_p2p_fuse", C.c_int, [_P, _P, _P, _P]),
     ("b200rag_p2p_close", C.c_int, [_P]),
+    ("b200rag_p2p_set_stream", C.c_int, [_P, _P]),
     ("b200rag_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200rag_get_stats_step", C.c_int, [_P, C.c_int32, C.POINTER(Stats)]),
     ("b200rag_set_profiling", C.c_int, [_P, C.c_int32]),
@@ -361,6 +362,9 @@ class Shard:
 
     def p2p_fuse(self, out_ids_dev, out_scores_dev, out_counts_dev):
         check(self._lib.b200rag_p2p_fuse(self._h, _ptr(out_ids_dev), _ptr(out_scores_dev), _ptr(out_counts_dev)))
+
+    def p2p_set_stream(self, stream_ptr):
+        check(self._lib.b200rag_p2p_set_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None))
 
     def p2p_close(self):
         check(self._lib.b200rag_p2p_close(self._h))

@@ -51,6 +51,15 @@ class ShardedSearcher:
         if self.world > 1 and device.type == "cuda" and hasattr(shard, "p2p_export") and \
                 os.environ.get("B200RAG_P2P", "1") != "0":
             self._setup_p2p()
+        # Pipelined tail: exchange + fuse run on their own stream, so the NEXT search's scans start while this search
+        # still waits for its slowest peer (and while its fuse runs).  Candidate and result buffers are double-buffered
+        # per parity; a buffer is reused only after the fuse that read it has finished.  OPT-IN (B200RAG_PIPELINE_TAIL=1):
+        # measured at 2 ranks only (10M hybrid top-10: 591 -> 607 q/s), not yet validated at 4 / 8 ranks.
+        self.pipeline = bool(self.p2p and os.environ.get("B200RAG_PIPELINE_TAIL", "0") == "1")
+        self._tail = None
+        if self.pipeline:
+            self._tail = torch.cuda.Stream(device=device)
+            self.shard.p2p_set_stream(self._tail.cuda_stream)
 
     def _setup_p2p(self):
         """Exchange CUDA IPC handles of the per-rank windows; every rank must succeed or all fall back to NCCL."""
@@ -91,8 +100,25 @@ class ShardedSearcher:
             b["host"] = torch.empty_like(b["out"], device="cpu")
             if self.device.type == "cuda":
                 b["host"] = b["host"].pin_memory()
+            if self.pipeline:
+                b["mine2"] = [b["mine"], torch.zeros_like(b["mine"])]
+                b["out2"] = [b["out"], torch.zeros_like(b["out"])]
+                b["legs_done"] = [torch.cuda.Event(), torch.cuda.Event()]
+                b["tail_done"] = [torch.cuda.Event(), torch.cuda.Event()]
+                b["used"] = [False, False]
+                b["n"] = 0
             self._bufs[key] = b
         return b
+
+    def result_stream(self):
+        """The stream on which a search's fused results become available (enqueue dependent work there)."""
+        if self._tail is not None:
+            return self._tail
+        return torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+
+    def record_end(self, event):
+        """Record a (timing) event at the point where the last enqueued search is complete."""
+        event.record(self.result_stream())
 
     def broadcast_query(self, arrays: dict | None, src: int = 0) -> dict:
         """Replicate a query batch from `src` (serving: the rank that received the request) to all ranks."""
@@ -128,6 +154,21 @@ class ShardedSearcher:
         nlegs, B, L, k = self._cur
         b = self._buffers(nlegs, B, L, k)
         mine, allb, out = b["mine"], b["all"], b["out"]
+        if self.pipeline and mine.numel() * 8 <= self.p2p_slot_bytes:
+            par = b["n"] & 1
+            b["n"] += 1
+            mine, out = b["mine2"][par], b["out2"][par]
+            main = torch.cuda.current_stream(self.device)
+            if b["used"][par]:
+                main.wait_event(b["tail_done"][par])       # the fuse two searches ago has released this parity's buffers
+            self.shard.legs(mine, mine[-1])
+            b["legs_done"][par].record(main)
+            self._tail.wait_event(b["legs_done"][par])
+            self.shard.p2p_exchange(mine, mine.numel() * 8)              # (the library launches these two on the
+            self.shard.p2p_fuse(out[:B * k], out[B * k:2 * B * k], out[2 * B * k:])   #  tail stream: p2p_set_stream)
+            b["tail_done"][par].record(self._tail)
+            b["used"][par] = True
+            return {"out": out, "host": b["host"], "tail": True}
         self.shard.legs(mine, mine[-1])                    # (legs zeroes the trailer's ambiguity counter itself)
         if self.world > 1 and self.p2p and mine.numel() * 8 <= self.p2p_slot_bytes:
             # peer stores into every rank's window + epoch flags; the fuse kernel waits for the flags itself
@@ -146,9 +187,14 @@ class ShardedSearcher:
     def fetch(self, b):
         """Device -> pinned host read-back of the fused results: (ids [B,k], scores [B,k] f64, counts [B], ambiguous)."""
         nlegs, B, L, k = self._cur
-        b["host"].copy_(b["out"], non_blocking=True)
-        if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
+        if b.get("tail"):
+            with torch.cuda.stream(self._tail):
+                b["host"].copy_(b["out"], non_blocking=True)
+            self._tail.synchronize()
+        else:
+            b["host"].copy_(b["out"], non_blocking=True)
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
         h = b["host"].numpy()
         ids = h[:B * k].reshape(B, k).copy()
         scores = h[B * k:2 * B * k].view(np.float64).reshape(B, k).copy()

@@ -996,8 +996,19 @@ int b200rag_p2p_exchange(b200rag_shard* sp, const void* mine, int64_t nbytes) {
     if (nbytes <= 0 || nbytes % 16 != 0 || nbytes > s->x_slot_bytes) { set_error("p2p_exchange: block does not fit the exchange slot"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
     ++s->x_epoch;
-    return launch_exchange(s, mine, nbytes, s->ws.xpeers_dev.as<void*>(), s->x_world, s->x_rank, s->x_slot_bytes,
-                           (int)(s->x_epoch & 1ull), s->x_epoch);
+    cudaStream_t keep = s->stream;
+    if (s->x_stream != nullptr) s->stream = s->x_stream;
+    const int rc = launch_exchange(s, mine, nbytes, s->ws.xpeers_dev.as<void*>(), s->x_world, s->x_rank, s->x_slot_bytes,
+                                   (int)(s->x_epoch & 1ull), s->x_epoch);
+    s->stream = keep;
+    return rc;
+}
+
+int b200rag_p2p_set_stream(b200rag_shard* sp, void* stream) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    s->x_stream = (cudaStream_t)stream;
+    return B200RAG_OK;
 }
 
 int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
@@ -1012,10 +1023,15 @@ int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, in
     const uint8_t* win = (const uint8_t*)s->xwin;
     const b200rag_cand* gathered = (const b200rag_cand*)(win + (size_t)(s->x_epoch & 1ull) * s->x_world * s->x_slot_bytes);
     const unsigned long long* flags = (const unsigned long long*)(win + (size_t)2 * s->x_world * s->x_slot_bytes);
-    B2_TRY(launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
-                       out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch));
-    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[5], s->stream)); s->ev_out = true; }
-    return B200RAG_OK;
+    cudaStream_t keep = s->stream;
+    if (s->x_stream != nullptr) s->stream = s->x_stream;
+    int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
+                         out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch);
+    if (rc == B200RAG_OK && s->profile) {
+        if (cudaEventRecord(s->ev[5], s->stream) == cudaSuccess) s->ev_out = true; else rc = cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    }
+    s->stream = keep;
+    return rc;
 }
 
 int b200rag_p2p_close(b200rag_shard* sp) {

@@ -177,6 +177,7 @@ struct Shard {
     int x_rank = 0, x_world = 0;
     int64_t x_slot_bytes = 0;
     unsigned long long x_epoch = 0;
+    cudaStream_t x_stream = nullptr;      // exchange + fuse stream (nullptr = the shard's stream)
 
     // pinned host staging for results
     void* h_pinned = nullptr;

@@ -492,6 +492,10 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the sparse leg's tail runs beside the dense scan: same carve-out, or it would wait for the scan's SMs to drain
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     if (sparse) leg_tail_kernel<true, 256><<<batch, 256, smem, s->stream>>>(p);
     else if (Lc > 64) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);   // 32 warps re-score in parallel
@@ -701,6 +705,11 @@ __global__ void __launch_bounds__(256) exchange_kernel(const uint4* __restrict__
 
 int launch_exchange(Shard* s, const void* mine, int64_t nbytes, void* const* peer_windows_dev, int world, int rank,
                     int64_t slot_bytes, int parity, unsigned long long epoch) {
+    // same shared-memory carve-out as the scan kernels: an SM cannot host CTAs of kernels with different carve-outs at
+    // the same time, and with the pipelined tail this kernel must co-reside with the next search's scan
+    static AttrCache attr;
+    if (attr.raise(s->cfg.device, 1))
+        B2_CUDA(cudaFuncSetAttribute(exchange_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     exchange_kernel<<<world, 256, 0, s->stream>>>(reinterpret_cast<const uint4*>(mine), nbytes / 16, peer_windows_dev, world,
                                                   rank, slot_bytes, parity, epoch);
     B2_CUDA(cudaGetLastError());
@@ -715,9 +724,11 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
     const size_t M = (size_t)next_pow2(n_shards * L);
     const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
     if (smem > 200 * 1024) { set_error("fuse: n_shards * L too large"); return B200RAG_ERR_INVALID; }
-    static AttrCache attr;
+    static AttrCache attr, carve;
     if (smem > 48 * 1024 && attr.raise(s->cfg.device, smem))
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (carve.raise(s->cfg.device, 1))     // co-resides with the next search's scan (see exchange_kernel)
+        B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
     const int fuse_threads = (size_t)n_shards * L > 512 ? 1024 : 256;     // the bitonic merge of large sets wants more lanes

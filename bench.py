@@ -274,8 +274,8 @@ def run_b200(a):
         ss.use_slot(i % n_slots)
         ev[i - W][0].record()
         b = ss.run_staged()
-        ev[i - W][1].record()
-    e_end.record()
+        ss.record_end(ev[i - W][1])              # (exchange + fuse may run on their own stream)
+    ss.record_end(e_end)
     barrier()
     wall_value = time.perf_counter() - wall0
     total_ms = float(e_begin.elapsed_time(e_end))

@@ -189,6 +189,10 @@ int b200rag_p2p_attach(b200rag_shard* s, int32_t rank, int32_t world, const uint
 int b200rag_p2p_exchange(b200rag_shard* s, const void* mine_dev, int64_t nbytes);
 int b200rag_p2p_fuse(b200rag_shard* s, int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
 int b200rag_p2p_close(b200rag_shard* s);
+/* Optional: launch exchange + fuse on `cuda_stream` instead of the shard's stream, so that a caller can let the NEXT
+ * search's scans start while this search still waits for its peers (the caller orders the two streams with events:
+ * exchange after this search's legs; buffers reused only after the fuse that read them).  NULL = the shard's stream. */
+int b200rag_p2p_set_stream(b200rag_shard* s, void* cuda_stream);
 
 /* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
 typedef struct {

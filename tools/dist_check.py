@@ -59,7 +59,8 @@ def main():
         b = ss.run_staged()
         if keep is None:
             keep = torch.empty((nst,) + tuple(b["out"].shape), dtype=b["out"].dtype, device=dev)
-        keep[i].copy_(b["out"], non_blocking=True)
+        with torch.cuda.stream(ss.result_stream()):
+            keep[i].copy_(b["out"], non_blocking=True)
     torch.cuda.synchronize(dev)
     hk = keep.cpu().numpy()
     for i in range(nst):
@@ -72,7 +73,7 @@ def main():
     tot = torch.tensor([bad], device=dev)
     dist.all_reduce(tot)
     if rank == 0:
-        print(f"dist_check world={world} p2p={ss.p2p}: mismatches={int(tot.item())}", flush=True)
+        print(f"dist_check world={world} p2p={ss.p2p} pipelined_tail={ss.pipeline}: mismatches={int(tot.item())}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(1 if int(tot.item()) else 0)
