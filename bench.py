@@ -35,6 +35,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "audio-rag_b200")]
 
+if any(x == "reference" or x.endswith("=reference") for x in sys.argv[1:]) and os.environ.get("RANK", "0") == "0":
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 ALONE (the others exit), so it
+    # gets every host core its BLAS can use.  Must happen before numpy loads its BLAS.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(_v) == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+            del os.environ[_v]
+
 import numpy as np  # noqa: E402
 
 SEED, QSEED = 1234, 2000
