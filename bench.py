@@ -51,8 +51,8 @@ METRIC = "hybrid top-10 queries/sec, 10Mx1024-d corpus"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
@@ -145,14 +145,24 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(self._kill)          # never leave the sampler behind, whatever ends the run
         except Exception:
             self.proc = None
 
+    def _kill(self):
+        try:
+            if self.proc is not None and self.proc.poll() is None:
+                self.proc.kill()
+        except Exception:
+            pass
+
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append([x.strip() for x in ln.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in ln.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (perf_counter; None = every sample)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -162,7 +172,10 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.06)]
+        if not rows:                      # a run shorter than one sampling period: the nearest samples are all there is
+            rows = [r for _, r in self.rows[-2:]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except Exception:
@@ -229,6 +242,13 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(str(torch.cuda.get_device_properties(dev).uuid))
+        if not sampler.uuid.startswith("GPU-"):
+            sampler.uuid = "GPU-" + sampler.uuid
+        sampler.start()       # nvidia-smi takes a while to deliver its first sample: it runs from here on, and only the
+                              # samples that arrive during the timed loops are summarised (ClockSampler.stop)
     lo, hi = shard_bounds(a.rows, world, rank, align=8192)
     t_build = time.time()
     sh = build_shard(a, dev, lo, hi)
@@ -251,12 +271,6 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = None
-    if rank == 0:
-        sampler = ClockSampler(str(torch.cuda.get_device_properties(dev).uuid))
-        if not sampler.uuid.startswith("GPU-"):
-            sampler.uuid = "GPU-" + sampler.uuid
-
     # ------------------------------------------------------------------ (1) device-resident timing -> value
     # Every step's query batch is staged into its own device slot BEFORE the timed region (inputs resident in HBM).
     # The K timed steps are then enqueued back to back -- legs -> candidate exchange -> fuse, no host synchronisation
@@ -267,8 +281,7 @@ def run_b200(a):
         f, ip, tt, ww = step_arrays(i)
         ss.stage(a.mode, a.top_k, normalize_bf16(f), ip, tt, ww, slot=i)
     barrier()
-    if sampler:
-        sampler.start()          # nvidia-smi needs ~0.1 s to deliver its first sample: start it before the warm-up steps
+    t_load0 = time.perf_counter()        # clocks are summarised from here (warm-up included) to the end of the e2e loop
     for i in range(W):
         ss.use_slot(i % n_slots)
         b = ss.run_staged()
@@ -317,7 +330,7 @@ def run_b200(a):
             e2e_t.append(time.perf_counter() - t0)
             h2d = max(h2d, B * a.dim * 2 + (B + 1) * 8 + len(tt) * 8 + B * 8)
     barrier()
-    clocks = sampler.stop() if sampler else None       # sampled across both timed loops (device-resident + e2e)
+    clocks = sampler.stop(t_load0, time.perf_counter()) if sampler else None   # both timed loops (device-resident + e2e)
     e2e_total = float(np.sum(e2e_t))
     d2h = B * a.top_k * 16 + (B + 1) * 4
     # the last e2e step and the last device-resident step used the same queries: results must agree
