@@ -85,8 +85,9 @@ class B200Retriever(BaseRetriever):
         self._hybrid_collections: set[str] = set()
         # host-side row bookkeeping
         self._payloads: list[dict] = []
-        self._row_coll: list[int] = []          # collection id per row
-        self._alive: list[bool] = []
+        self._row_coll = np.zeros(0, dtype=np.int32)   # collection id per row   } views of length len(_payloads) into
+        self._alive = np.zeros(0, dtype=bool)          # tombstones              } buffers that grow by doubling
+        self._row_cap = (np.zeros(1024, dtype=np.int32), np.zeros(1024, dtype=bool))
         self._coll_ids: dict[str, int] = {}
         self._coll_rows: dict[str, int] = {}    # live rows per collection
         self._coll_version: dict[str, int] = {}
@@ -111,6 +112,28 @@ class B200Retriever(BaseRetriever):
         if self._shard is not None:
             self._shard.close()
             self._shard = None
+
+    def _set_rows(self, coll, alive) -> None:
+        """Replace the per-row bookkeeping (load / clear)."""
+        n = len(coll)
+        cap = max(1024, 1 << int(n - 1).bit_length()) if n else 1024
+        self._row_cap = (np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=bool))
+        self._row_cap[0][:n], self._row_cap[1][:n] = coll, alive
+        self._row_coll, self._alive = self._row_cap[0][:n], self._row_cap[1][:n]
+
+    def _append_rows(self, cid: int, n_new: int) -> None:
+        """n_new live rows of collection `cid` at the end of the row space (amortised O(1) per row)."""
+        n = len(self._row_coll)
+        if n + n_new > len(self._row_cap[0]):
+            cap = len(self._row_cap[0])
+            while cap < n + n_new:
+                cap *= 2
+            grown = (np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=bool))
+            grown[0][:n], grown[1][:n] = self._row_coll, self._alive
+            self._row_cap = grown
+        self._row_cap[0][n:n + n_new] = cid
+        self._row_cap[1][n:n + n_new] = True
+        self._row_coll, self._alive = self._row_cap[0][:n + n_new], self._row_cap[1][:n + n_new]
 
     def _resolve_collection(self, collection_name: str | None) -> str:
         return collection_name or self.config.collection_name
@@ -176,8 +199,7 @@ class B200Retriever(BaseRetriever):
             self._get_shard().add(bits, indptr, terms, weights)
             cid = self._coll_ids[resolved]
             self._payloads.extend(payloads)
-            self._row_coll.extend([cid] * len(chunks))
-            self._alive.extend([True] * len(chunks))
+            self._append_rows(cid, len(chunks))
             self._coll_rows[resolved] += len(chunks)
             self._coll_version[resolved] += 1
             logger.info(f"Added {len(chunks)} chunks to {resolved} (hybrid={is_hybrid})")
@@ -193,7 +215,7 @@ class B200Retriever(BaseRetriever):
         if not filter_metadata and self._coll_rows.get(resolved, 0) == n:
             return None
         cid = self._coll_ids[resolved]
-        elig = (np.asarray(self._row_coll, dtype=np.int64) == cid) & np.asarray(self._alive, dtype=bool)
+        elig = (self._row_coll == cid) & self._alive
         if filter_metadata:
             for r in np.flatnonzero(elig):
                 meta = self._payloads[r].get("metadata")
@@ -354,18 +376,15 @@ class B200Retriever(BaseRetriever):
         try:
             if resolved in self._existing_collections:
                 cid = self._coll_ids[resolved]
-                for r, c in enumerate(self._row_coll):
-                    if c == cid:
-                        self._alive[r] = False
+                self._alive[self._row_coll == cid] = False
                 self._coll_rows[resolved] = 0
                 self._coll_version[resolved] += 1
-                if not any(self._alive):
+                if not self._alive.any():
                     # nothing live anywhere: drop the rows for real
                     if self._shard is not None:
                         self._shard.clear()
                     self._payloads.clear()
-                    self._row_coll.clear()
-                    self._alive.clear()
+                    self._set_rows([], [])
                     self._masks.clear()
             self._existing_collections.discard(resolved)
             self._hybrid_collections.discard(resolved)
@@ -392,7 +411,7 @@ class B200Retriever(BaseRetriever):
                                        "exists": name in self._existing_collections,
                                        "live_rows": self._coll_rows.get(name, 0)}
                                 for name, cid in self._coll_ids.items()},
-                "row_collection": self._row_coll, "alive": [int(a) for a in self._alive],
+                "row_collection": self._row_coll.tolist(), "alive": self._alive.astype(int).tolist(),
             }
             with open(os.path.join(directory, "manifest.json"), "w", encoding="utf-8") as f:
                 json.dump(manifest, f)
@@ -420,8 +439,7 @@ class B200Retriever(BaseRetriever):
                 raise RetrievalError("shard.bin holds a different number of rows than the manifest")
             self._row_base = m["row_base"]
             self._payloads = payloads
-            self._row_coll = [int(c) for c in m["row_collection"]]
-            self._alive = [bool(a) for a in m["alive"]]
+            self._set_rows(np.asarray(m["row_collection"], dtype=np.int32), np.asarray(m["alive"], dtype=bool))
             for name, c in m["collections"].items():
                 self._coll_ids[name] = int(c["id"])
                 self._coll_rows[name] = int(c["live_rows"])

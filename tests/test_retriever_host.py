@@ -161,6 +161,40 @@ def test_search_batch_arrays_matches_search_batch():
     assert arr["counts"][3] == 0 and (arr["ids"][3] == -1).all()
 
 
+def test_row_bookkeeping_grows_and_tombstones():
+    """The per-row bookkeeping (collection id, tombstone) lives in growable arrays: many small adds beyond the initial
+    capacity, interleaved tenants, delete + re-add, and the drop of the storage once nothing is live."""
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever
+    A, E, S = _types()
+    r = B200Retriever(RetrievalConfig(top_k=3), embedding_dim=DIM)
+    r._shard = OracleShard(dim=DIM)
+    ch, em = make_chunks(150, 71, "G", A, E, S, sparse=False)
+    total = {"g0": 0, "g1": 0, "g2": 0}
+    for rep in range(24):                                   # 3 600 rows in 24 adds: crosses the 1024 and 2048 capacities
+        name = f"g{rep % 3}"
+        r.add(ch, em, name)
+        total[name] += 150
+    assert len(r._row_coll) == len(r._alive) == len(r._payloads) == 3600 and r._alive.all()
+    assert [r.count(n) for n in total] == [1200, 1200, 1200]
+    assert (r._row_coll[:450] == np.repeat([0, 1, 2], 150)).all()
+    e1 = r._eligible("g1", None)
+    assert e1.sum() == 1200 and e1[150:300].all() and not e1[:150].any()
+    q = make_queries(1, 72, 150, 71, E, S, sparse=False)[0]
+    hits = r.search(q, collection_name="g1", top_k=3)
+    assert len(hits) == 3 and all(h.source == "g1" for h in hits)
+    r.delete_collection("g1")
+    assert r.count("g1") == 0 and r._alive.sum() == 2400 and not r._alive[150:300].any()
+    assert r.search(q, collection_name="g1", top_k=3) == []
+    r.add(ch[:10], em[:10], "g1")                            # the name is reusable; old rows stay tombstoned
+    assert r.count("g1") == 10 and r._eligible("g1", None).sum() == 10 and len(r._row_coll) == 3610
+    for n in ("g0", "g1", "g2"):
+        r.delete_collection(n)
+    assert len(r._row_coll) == len(r._alive) == len(r._payloads) == 0 and r._shard.count == 0
+    r.add(ch[:5], em[:5], "g0")
+    assert r.count("g0") == 5 and len(r.search(q, collection_name="g0", top_k=3)) == 3
+
+
 def test_save_load_host_logic(tmp_path):
     """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
     retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
