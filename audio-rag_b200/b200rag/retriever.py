@@ -92,6 +92,7 @@ class B200Retriever(BaseRetriever):
         self._coll_rows: dict[str, int] = {}    # live rows per collection
         self._coll_version: dict[str, int] = {}
         self._masks: OrderedDict = OrderedDict()  # (collection, filter key) -> (mask_id, version)
+        self._meta_index: dict = {}               # metadata key -> {"upto": rows indexed, "map": value -> [rows], "slow": [rows]}
         self._next_mask = 0
         logger.info(f"B200Retriever initialized: collection={config.collection_name}, "
                     f"search_type={config.search_type}")
@@ -216,12 +217,38 @@ class B200Retriever(BaseRetriever):
             return None
         cid = self._coll_ids[resolved]
         elig = (self._row_coll == cid) & self._alive
-        if filter_metadata:
-            for r in np.flatnonzero(elig):
-                meta = self._payloads[r].get("metadata")
-                if not all(_match(meta, k, v) for k, v in filter_metadata.items()):
-                    elig[r] = False
+        for k, v in (filter_metadata or {}).items():
+            hit = np.zeros(n, dtype=bool)
+            hit[self._meta_rows(k, v)] = True
+            elig &= hit
         return elig
+
+    def _meta_rows(self, key, value) -> np.ndarray:
+        """Rows (of any collection) whose ``metadata[key]`` matches ``value`` under ``_match``.  A per-key payload
+        index (value -> rows, list-valued fields indexed by element) is built on the first filter that names the key
+        and extended as rows are added -- the host-side analogue of a qdrant payload index, so that a new filter costs
+        one lookup instead of a Python pass over every payload."""
+        idx = self._meta_index.setdefault(key, {"upto": 0, "map": {}, "slow": []})
+        for r in range(idx["upto"], len(self._payloads)):
+            meta = self._payloads[r].get("metadata")
+            if not isinstance(meta, dict) or key not in meta:
+                continue
+            got = meta[key]
+            try:
+                for item in (got if isinstance(got, (list, tuple)) else (got,)):
+                    rows = idx["map"].setdefault(item, [])
+                    if not rows or rows[-1] != r:
+                        rows.append(r)
+            except TypeError:                     # unhashable stored value: matched the slow way
+                idx["slow"].append(r)
+        idx["upto"] = len(self._payloads)
+        try:
+            rows = list(idx["map"].get(value, ()))
+            slow = idx["slow"]
+        except TypeError:                         # unhashable filter value: every row that has the key is a candidate
+            rows, slow = [], sorted({r for rr in idx["map"].values() for r in rr} | set(idx["slow"]))
+        rows += [r for r in slow if _match(self._payloads[r].get("metadata"), key, value)]
+        return np.asarray(rows, dtype=np.int64)
 
     def _mask_id(self, resolved: str, filter_metadata: dict | None) -> int:
         elig_key = (resolved, tuple(sorted((str(k), repr(v)) for k, v in (filter_metadata or {}).items())))
@@ -386,6 +413,7 @@ class B200Retriever(BaseRetriever):
                     self._payloads.clear()
                     self._set_rows([], [])
                     self._masks.clear()
+                    self._meta_index.clear()
             self._existing_collections.discard(resolved)
             self._hybrid_collections.discard(resolved)
             logger.info(f"Deleted collection: {resolved}")
@@ -449,6 +477,7 @@ class B200Retriever(BaseRetriever):
                 if c["hybrid"]:
                     self._hybrid_collections.add(name)
             self._masks.clear()
+            self._meta_index.clear()
         except RetrievalError as e:
             raise RetrievalError(f"Failed to load retriever from '{directory}': {e}")
         except Exception as e:

@@ -195,6 +195,38 @@ def test_row_bookkeeping_grows_and_tombstones():
     assert r.count("g0") == 5 and len(r.search(q, collection_name="g0", top_k=3)) == 3
 
 
+def test_payload_index_equals_per_row_matching():
+    """filter_metadata goes through a per-key payload index (value -> rows); it must select exactly the rows the
+    per-payload rule `_match` (FieldCondition + MatchValue, qdrant.py:264-268) selects -- list-valued fields, mixed
+    numeric types, None, unhashable stored values and unhashable filter values included -- also after further adds."""
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever, _match
+    A, E, S = _types()
+    r = B200Retriever(RetrievalConfig(top_k=3), embedding_dim=DIM)
+    r._shard = OracleShard(dim=DIM)
+    ch, em = make_chunks(60, 81, "P", A, E, S, sparse=False)
+    odd = [1, 1.0, True, 0, False, None, "1", ["a", "b"], ("a",), [], {"x": 1}, [1, {"y": 2}], "a", 2.5]
+    for i, c in enumerate(ch):
+        c.metadata = dict(c.metadata)
+        if i % 5 != 4:
+            c.metadata["odd"] = odd[i % len(odd)]
+    probes = [1, True, 0, None, "1", "a", "b", 2.5, {"x": 1}, {"y": 2}, ["a", "b"], "zzz"]
+
+    def brute(key, value):
+        return [i for i, p in enumerate(r._payloads) if _match(p.get("metadata"), key, value)]
+
+    r.add(ch[:35], em[:35], "p")
+    for v in probes:
+        assert sorted(set(r._meta_rows("odd", v).tolist())) == brute("odd", v), v
+    r.add(ch[35:], em[35:], "p")                          # the index is extended, not rebuilt
+    for v in probes:
+        assert sorted(set(r._meta_rows("odd", v).tolist())) == brute("odd", v), v
+        elig = r._eligible("p", {"odd": v, "lang": "en"})
+        want = [i for i in brute("odd", v) if i in set(brute("lang", "en"))]
+        assert np.flatnonzero(elig).tolist() == want, v
+    assert r._meta_rows("absent", 1).size == 0
+
+
 def test_save_load_host_logic(tmp_path):
     """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
     retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
