@@ -227,6 +227,47 @@ def test_payload_index_equals_per_row_matching():
     assert r._meta_rows("absent", 1).size == 0
 
 
+def test_random_operation_sequences_match_reference_plugin():
+    """Seeded random sequences of add / delete_collection / search over three tenants, with enough distinct
+    (collection, filter) pairs to push masks out of the 64-entry cache and back: after every operation the reference's
+    own plugin (over the qdrant_client double) and B200Retriever must agree on results, counts and existence."""
+    import random
+    A, E, S = _types()
+    for seed in (1, 2):
+        rng = random.Random(seed)
+        ref, ours = _pair(top_k=4)
+        names = ["ta", "tb", "legacy"]
+        pool = {n: make_chunks(90, 40 + i, n.upper(), A, E, S, sparse=(n != "legacy")) for i, n in enumerate(names)}
+        cursor = {n: 0 for n in names}
+        qs = make_queries(6, 50 + seed, 90, 40, E, S) + make_queries(2, 60 + seed, 90, 42, E, S, sparse=False)
+        filters = [None] + [{"idx": i} for i in range(80)] + [{"lang": "en"}, {"lang": "de"}, {"tags": "a"},
+                                                              {"tags": "c", "lang": "de"}, {"source": "TA-1.wav"}]
+        for step in range(330):
+            op = rng.random()
+            name = rng.choice(names)
+            if op < 0.15 and cursor[name] < 90:
+                n = min(rng.choice([1, 7, 20]), 90 - cursor[name])
+                ch, em = pool[name]
+                sl = slice(cursor[name], cursor[name] + n)
+                ref.add(ch[sl], em[sl], name)
+                ours.add(ch[sl], em[sl], name)
+                cursor[name] += n
+            elif op < 0.17:
+                ref.delete_collection(name)
+                ours.delete_collection(name)
+                cursor[name] = 0                       # the same chunks may be added again (new rows, new ids)
+            else:
+                q = rng.choice(qs)
+                kw = {"search_type": rng.choice(["dense", "sparse", "hybrid", None]), "top_k": rng.choice([None, 1, 9]),
+                      "filter_metadata": rng.choice(filters) if rng.random() < 0.8 else None}
+                a = result_rows(ref.search(q, collection_name=name, **kw))
+                b = result_rows(ours.search(q, collection_name=name, **kw))
+                assert a == b, (seed, step, name, kw, a[:2], b[:2])
+            for n in names:
+                assert ref.count(n) == ours.count(n)
+        assert len(ours._masks) <= 64 < ours._next_mask          # the cache did overflow and evict
+
+
 def test_save_load_host_logic(tmp_path):
     """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
     retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
