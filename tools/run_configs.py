@@ -73,7 +73,7 @@ def run(sh, dev, rows_total, mode, B, top_k, iters, mask_ids=None, label=""):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
-    ap.add_argument("--only", default="c2,c3,c4,c5")
+    ap.add_argument("--only", default="c1,c2,c3,c4,c5")
     a = ap.parse_args()
     only = a.only.split(",")
     dev = torch.device("cuda", 0)
@@ -85,6 +85,43 @@ def main():
         sh.set_profiling(True)
         return sh
 
+    if "c1" in only:       # the reference's own CPU-runnable case: hybrid top-5 over 10k chunks, single query
+        n = 10_000
+        sh = shard(n, True)
+        r = run(sh, dev, n, "hybrid", 1, 5, 200, label="config1 hybrid top-5, 10k chunks, single query")
+        # the same call through the host-buffer C ABI (wall clock), and the reference-shaped CPU port on the box's
+        # host cores over the SAME 10k rows (no scaling) -- the oracle here is the thing timed as a baseline, never
+        # part of the measured GPU path
+        nq = 40
+        qf = synth.dense_queries_f32(2000, 0, nq, n, sh.dim, corpus_seed=1234)
+        ip, tt, ww = synth.sparse_queries(2000, 0, nq)
+        wall = []
+        for i in range(nq):
+            t0 = time.perf_counter()
+            sh.search("hybrid", 5, normalize_bf16(qf[i:i + 1]), ip[i:i + 2] - ip[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]])
+            wall.append(time.perf_counter() - t0)
+        r["e2e_p50_ms"] = float(np.median(wall[5:]) * 1e3)
+        try:
+            from oracle import fast, oracle
+            dense = synth.bf16_bits_to_f32(fast.synth_dense_bf16(1234, 0, n, sh.dim))
+            thr_h = synth.zipf_thresholds(synth.VOCAB)
+            idf, tff = synth.bm25_tables(n)
+            dip, dtt, dww = fast.synth_sparse_csr(1234, 0, n, thr_h, idf, tff, synth.VOCAB, 256, synth.TERM_PERM_MUL)
+            ref = oracle.RefShapedIndex(dense, dip, dtt, dww)
+            cpu = []
+            for i in range(12):
+                t0 = time.perf_counter()
+                ref.hybrid(qf[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]], None, 5)
+                cpu.append(time.perf_counter() - t0)
+            r["cpu_port_p50_ms"] = float(np.median(cpu[2:]) * 1e3)
+            r["cpu_port_note"] = ("oracle.RefShapedIndex (fp32 sgemv + argsort, Python two-pointer loop per document, dict "
+                                  f"RRF: the shape of qdrant-client local mode) on {os.cpu_count()} host cpus, same 10k rows")
+        except Exception as e:      # a missing checker never fails the measurement
+            r["cpu_port_note"] = f"not timed: {e}"
+        print(json.dumps({k: r[k] for k in r if k.startswith(("e2e", "cpu_port"))}), flush=True)
+        res.append(r)
+        sh.close()
+        torch.cuda.empty_cache()
     if "c2" in only:       # dense-only exact top-10 over 1M x 1024 bf16, B = 1 and 256, 1 x B200
         sh = shard(1_000_000, False)
         res.append(run(sh, dev, 1_000_000, "dense", 1, 10, 50, label="config2 dense top-10 1M B=1"))
