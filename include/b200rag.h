@@ -166,7 +166,9 @@ int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, i
  * One file per shard: header | dense bf16 rows | forward sparse index (indptr, terms, weights).  The inverted index,
  * directories and the weight bound are rebuilt on load (~0.2 s per 10M rows) so the file has no layout the kernels
  * depend on.  `load` needs an EMPTY shard created with the same dim and vocab; masks and payloads are the plugin's
- * (B200Retriever.save/load write them next to this file).  Returns B200RAG_ERR_INVALID on a foreign/corrupt file. */
+ * (B200Retriever.save/load write them next to this file).  Returns B200RAG_ERR_INVALID on a foreign, mismatching
+ * (dim / vocab) or truncated file; the CONTENT of a file that passes those checks is trusted like the arguments of
+ * b200rag_add are (indptr monotone, terms ascending and < vocab) -- it is this library's own output. */
 int b200rag_save(b200rag_shard* s, const char* path);
 int b200rag_load(b200rag_shard* s, const char* path);
 
