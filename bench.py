@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--mode", default="hybrid", choices=["dense", "sparse", "hybrid"])
     ap.add_argument("--query-tokens", type=int, default=12)
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000)
-    ap.add_argument("--cpu-queries", type=int, default=16)
+    ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
