@@ -100,6 +100,26 @@ def cpu_reference(a, steps, warmup, sample_rows):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     per_query_sample = float(np.mean(times))
+    # once with the default BLAS threads (above), once pinned to one thread (a few queries are enough: the
+    # single-threaded Python sparse loop dominates either way)
+    one_thread_ms = None
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            t1 = []
+            for i in range(warmup, min(nq, warmup + 4)):
+                sl = slice(qi[i], qi[i + 1])
+                t0 = time.perf_counter()
+                if a.mode == "hybrid":
+                    ref.hybrid(qf[i], qt[sl], qw[sl], None, a.top_k)
+                elif a.mode == "dense":
+                    ref.dense_leg(qf[i], None, a.top_k)
+                else:
+                    ref.sparse_leg(qt[sl], qw[sl], None, a.top_k)
+                t1.append(time.perf_counter() - t0)
+            one_thread_ms = float(np.mean(t1) * 1e3)
+    except Exception:
+        pass
     scale = a.rows / n
     qps = 1.0 / (per_query_sample * scale)
     try:
@@ -112,7 +132,9 @@ def cpu_reference(a, steps, warmup, sample_rows):
                         f"({per_query_sample * 1e3:.1f} ms/query on the slice; BLAS sgemv uses {blas_threads} threads, "
                         f"the per-document sparse loop is single-threaded Python as in qdrant-client local mode), "
                         f"scaled x{scale:.0f} linearly to {a.rows} rows",
-              "p50_ms_on_sample": float(np.median(times) * 1e3), "host_cpus": os.cpu_count()}
+              "p50_ms_on_sample": float(np.median(times) * 1e3), "host_cpus": os.cpu_count(),
+              "affinity_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+              "ms_on_sample_blas_1_thread": one_thread_ms}
     return qps, detail, per_query_sample * scale * 1e3
 
 
