@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200rag.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NOGPU, ERR_OOM, ERR_STATE = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_NOGPU, ERR_OOM, ERR_STATE, ERR_INEXACT = range(7)
 DENSE, SPARSE, HYBRID = 0, 1, 2
 MODES = {"dense": DENSE, "sparse": SPARSE, "hybrid": HYBRID}
 MAX_TOPK = 256
@@ -51,7 +51,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int32), ("dense_path", C.c_int32), ("dense_bytes", C.c_int64),
                 ("sparse_postings", C.c_int64), ("dense_passes", C.c_int32), ("retries", C.c_int32),
                 ("dense_scan_ms", C.c_float), ("sparse_scan_ms", C.c_float),
-                ("pre_scan_ms", C.c_float), ("tail_ms", C.c_float)]
+                ("pre_scan_ms", C.c_float), ("tail_ms", C.c_float), ("exhaustive", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/b200rag.h declares: (name, restype, argtypes)
@@ -65,16 +65,24 @@ SYMBOLS = [
     ("b200rag_shard_destroy", None, [_P]),
     ("b200rag_set_stream", C.c_int, [_P, _P]),
     ("b200rag_set_slack", C.c_int, [_P, C.c_int32]),
+    ("b200rag_set_exhaustive", C.c_int, [_P, C.c_int32]),
+    ("b200rag_set_exact_fallback", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_dense_path", C.c_int, [_P, C.c_int32]),
     ("b200rag_debug_dense_scores", C.c_int, [_P, _P]),
     ("b200rag_sync", C.c_int, [_P]),
     ("b200rag_add", C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     ("b200rag_add_device", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64]),
+    ("b200rag_add_ids", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    ("b200rag_add_device_ids", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
+    ("b200rag_add_f32", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    ("b200rag_compact", C.c_int, [_P, _P, C.c_int64]),
     ("b200rag_build", C.c_int, [_P]),
     ("b200rag_count", C.c_int64, [_P]),
     ("b200rag_postings", C.c_int64, [_P]),
     ("b200rag_clear", C.c_int, [_P]),
     ("b200rag_read_dense", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    ("b200rag_read_sparse", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64]),
+    ("b200rag_read_row_ids", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("b200rag_mask_set", C.c_int, [_P, C.c_int32, _P, C.c_int64]),
     ("b200rag_mask_set_device", C.c_int, [_P, C.c_int32, _P, C.c_int64]),
     ("b200rag_mask_drop", C.c_int, [_P, C.c_int32]),
@@ -95,6 +103,11 @@ SYMBOLS = [
     ("b200rag_p2p_fuse", C.c_int, [_P, _P, _P, _P]),
     ("b200rag_p2p_close", C.c_int, [_P]),
     ("b200rag_p2p_set_stream", C.c_int, [_P, _P]),
+    ("b200rag_group_create", C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
+    ("b200rag_group_destroy", None, [_P]),
+    ("b200rag_group_size", C.c_int32, [_P]),
+    ("b200rag_group_search", C.c_int, [_P, C.POINTER(Query), _P, _P, _P]),
+    ("b200rag_group_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200rag_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200rag_get_stats_step", C.c_int, [_P, C.c_int32, C.POINTER(Stats)]),
     ("b200rag_set_profiling", C.c_int, [_P, C.c_int32]),
@@ -183,21 +196,46 @@ class Shard:
             pass
 
     # ---- ingest
-    def add(self, dense_bits: np.ndarray, sp_indptr=None, sp_terms=None, sp_weights=None):
-        dense_bits = np.ascontiguousarray(dense_bits, dtype=np.uint16).reshape(-1, self.dim)
-        n = dense_bits.shape[0]
+    @staticmethod
+    def _csr(n, sp_indptr, sp_terms, sp_weights, ids):
         if sp_indptr is not None:
             sp_indptr = np.ascontiguousarray(sp_indptr, dtype=np.int64)
             sp_terms = np.ascontiguousarray(sp_terms, dtype=np.uint32)
             sp_weights = np.ascontiguousarray(sp_weights, dtype=np.float32)
             if len(sp_indptr) != n + 1:
                 raise B200RagError(ERR_INVALID, "sparse indptr length must be n+1")
-        check(self._lib.b200rag_add(self._h, n, _np_ptr(dense_bits), _np_ptr(sp_indptr), _np_ptr(sp_terms),
-                                    _np_ptr(sp_weights)))
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            if len(ids) != n:
+                raise B200RagError(ERR_INVALID, "one row id per row expected")
+        return sp_indptr, sp_terms, sp_weights, ids
 
-    def add_device(self, n, dense_bits_dev, sp_indptr_dev=None, sp_terms_dev=None, sp_weights_dev=None, nnz=0):
-        check(self._lib.b200rag_add_device(self._h, n, _ptr(dense_bits_dev), _ptr(sp_indptr_dev), _ptr(sp_terms_dev),
-                                           _ptr(sp_weights_dev), nnz))
+    def add(self, dense_bits: np.ndarray, sp_indptr=None, sp_terms=None, sp_weights=None, ids=None):
+        """Append unit bf16 rows (+ their sparse parts); `ids` = global row ids (None: row_base + local row)."""
+        dense_bits = np.ascontiguousarray(dense_bits, dtype=np.uint16).reshape(-1, self.dim)
+        n = dense_bits.shape[0]
+        sp_indptr, sp_terms, sp_weights, ids = self._csr(n, sp_indptr, sp_terms, sp_weights, ids)
+        check(self._lib.b200rag_add_ids(self._h, n, _np_ptr(dense_bits), _np_ptr(sp_indptr), _np_ptr(sp_terms),
+                                        _np_ptr(sp_weights), _np_ptr(ids)))
+
+    def add_f32(self, dense_f32: np.ndarray, sp_indptr=None, sp_terms=None, sp_weights=None, ids=None):
+        """Append RAW fp32 rows: normalised + rounded to bf16 on the GPU (bit-equal to normalize_bf16 + add)."""
+        dense_f32 = np.ascontiguousarray(dense_f32, dtype=np.float32).reshape(-1, self.dim)
+        n = dense_f32.shape[0]
+        sp_indptr, sp_terms, sp_weights, ids = self._csr(n, sp_indptr, sp_terms, sp_weights, ids)
+        check(self._lib.b200rag_add_f32(self._h, n, _np_ptr(dense_f32), _np_ptr(sp_indptr), _np_ptr(sp_terms),
+                                        _np_ptr(sp_weights), _np_ptr(ids)))
+
+    def add_device(self, n, dense_bits_dev, sp_indptr_dev=None, sp_terms_dev=None, sp_weights_dev=None, nnz=0, ids=None):
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+        check(self._lib.b200rag_add_device_ids(self._h, n, _ptr(dense_bits_dev), _ptr(sp_indptr_dev),
+                                               _ptr(sp_terms_dev), _ptr(sp_weights_dev), nnz, _np_ptr(ids)))
+
+    def compact(self, keep_words: np.ndarray, n_rows: int):
+        """Physically drop the local rows whose keep bit is clear (ids and order of the others are preserved)."""
+        keep_words = np.ascontiguousarray(keep_words, dtype=np.uint32)
+        check(self._lib.b200rag_compact(self._h, _np_ptr(keep_words), n_rows))
 
     def build(self):
         check(self._lib.b200rag_build(self._h))
@@ -218,6 +256,22 @@ class Shard:
         check(self._lib.b200rag_read_dense(self._h, row, n, _np_ptr(out)))
         return out
 
+    def read_sparse(self, row: int, n: int):
+        """(indptr int64[n+1] from 0, terms uint32, weights float32) of the stored rows [row, row + n)."""
+        indptr = np.empty(n + 1, dtype=np.int64)
+        check(self._lib.b200rag_read_sparse(self._h, row, n, _np_ptr(indptr), None, None, 0))
+        nnz = int(indptr[n])
+        terms = np.empty(nnz, dtype=np.uint32)
+        w = np.empty(nnz, dtype=np.float32)
+        if nnz:
+            check(self._lib.b200rag_read_sparse(self._h, row, n, _np_ptr(indptr), _np_ptr(terms), _np_ptr(w), nnz))
+        return indptr, terms, w
+
+    def read_row_ids(self, row: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int64)
+        check(self._lib.b200rag_read_row_ids(self._h, row, n, _np_ptr(out)))
+        return out
+
     # ---- masks
     def mask_set(self, mask_id: int, words, n_rows: int):
         if isinstance(words, np.ndarray):
@@ -236,6 +290,14 @@ class Shard:
 
     def set_slack(self, slack: int):
         check(self._lib.b200rag_set_slack(self._h, slack))
+
+    def set_exhaustive(self, on: bool):
+        """Legs score EVERY eligible row canonically and sort: always exact (fallback + cross-check path)."""
+        check(self._lib.b200rag_set_exhaustive(self._h, 1 if on else 0))
+
+    def set_exact_fallback(self, on: bool):
+        """Off: a search whose slack guard never clears raises B200RagError(ERR_INEXACT) instead of falling back."""
+        check(self._lib.b200rag_set_exact_fallback(self._h, 1 if on else 0))
 
     def set_dense_path(self, path: int):
         """0 = auto, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM."""
@@ -399,3 +461,44 @@ class Shard:
     def synth_collection_mask(self, seed, global_row_start, n, thr_dev, n_collections, collection, out_words_dev):
         check(self._lib.b200rag_synth_collection_mask(self._h, seed, global_row_start, n, _ptr(thr_dev),
                                                       n_collections, collection, _ptr(out_words_dev)))
+
+
+class ShardGroup:
+    """Several shards of one corpus driven by this process (b200rag_group_*): `search` is `Shard.search` over all of
+    them, bit-identical to one shard holding every row.  The shards stay owned by the caller."""
+
+    def __init__(self, shards):
+        self._lib = load()
+        self.shards = list(shards)
+        self.dim = self.shards[0].dim
+        arr = (_P * len(self.shards))(*[s._h for s in self.shards])
+        h = C.c_void_p()
+        check(self._lib.b200rag_group_create(arr, len(self.shards), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200rag_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, mode, top_k, q_bits=None, sp_indptr=None, sp_terms=None, sp_weights=None, mask_ids=None,
+               score_threshold=None, rrf_k=0):
+        q, keep = self.shards[0].make_query(mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids,
+                                            score_threshold, rrf_k)
+        ids = np.empty((q.batch, top_k), dtype=np.int64)
+        scores = np.empty((q.batch, top_k), dtype=np.float64)
+        counts = np.empty(q.batch, dtype=np.int32)
+        check(self._lib.b200rag_group_search(self._h, C.byref(q), _np_ptr(ids), _np_ptr(scores), _np_ptr(counts)))
+        del keep
+        return ids, scores, counts
+
+    def stats(self) -> dict:
+        st = Stats()
+        check(self._lib.b200rag_group_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}

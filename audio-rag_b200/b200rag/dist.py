@@ -26,6 +26,9 @@ import torch.distributed as dist
 from ._ffi import Shard
 
 
+PIPELINE_TAIL_DEFAULT = "0"
+
+
 def shard_bounds(n_total: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
     """Contiguous row range of `rank` (balanced; starts aligned to `align` rows)."""
     per = -(-n_total // world)
@@ -46,6 +49,14 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs: dict = {}
         self._slots: dict = {}
+        self.broken = None          # reason, once an exchange timed out (the ranks' epochs have diverged: reset())
+        # Everything this class enqueues besides the library's kernels -- the buffers' zero fills, the NCCL all-gather,
+        # the result read-back, the pipelined tail's events -- runs on torch's CURRENT stream.  A Shard runs on a
+        # private stream until told otherwise, which would leave the two unordered (results read before the fuse
+        # finished, candidates gathered before the legs).  So the shard is tied to torch's current stream here.
+        if device.type == "cuda" and hasattr(shard, "set_stream"):
+            shard.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        self.exact_fallback = os.environ.get("B200RAG_EXACT_FALLBACK", "1") != "0"
         self.p2p = False
         self.p2p_slot_bytes = int(os.environ.get("B200RAG_P2P_SLOT_BYTES", 8 << 20))
         if self.world > 1 and device.type == "cuda" and hasattr(shard, "p2p_export") and \
@@ -53,9 +64,8 @@ class ShardedSearcher:
             self._setup_p2p()
         # Pipelined tail: exchange + fuse run on their own stream, so the NEXT search's scans start while this search
         # still waits for its slowest peer (and while its fuse runs).  Candidate and result buffers are double-buffered
-        # per parity; a buffer is reused only after the fuse that read it has finished.  OPT-IN (B200RAG_PIPELINE_TAIL=1):
-        # measured at 2 ranks only (10M hybrid top-10: 591 -> 607 q/s), not yet validated at 4 / 8 ranks.
-        self.pipeline = bool(self.p2p and os.environ.get("B200RAG_PIPELINE_TAIL", "0") == "1")
+        # per parity; a buffer is reused only after the fuse that read it has finished.  B200RAG_PIPELINE_TAIL=0/1.
+        self.pipeline = bool(self.p2p and os.environ.get("B200RAG_PIPELINE_TAIL", PIPELINE_TAIL_DEFAULT) == "1")
         self._tail = None
         if self.pipeline:
             self._tail = torch.cuda.Stream(device=device)
@@ -94,8 +104,9 @@ class ShardedSearcher:
             b = {
                 "mine": torch.zeros((n, 2), dtype=torch.int64, device=self.device),
                 "all": torch.zeros((self.world, n, 2), dtype=torch.int64, device=self.device),
-                # ids | scores(f64 bits) | counts(+flag) in ONE buffer -> one D2H per batch
-                "out": torch.zeros(2 * B * k + (B + 2) // 2 + 1, dtype=torch.int64, device=self.device),
+                # ids | scores(f64 bits) | counts [B] + ambiguity counter + sticky timeout latch, in ONE buffer -> one
+                # D2H per batch (zeroed once here: the latch is only ever set by a fuse that gave up on a peer)
+                "out": torch.zeros(2 * B * k + (B + 3) // 2 + 1, dtype=torch.int64, device=self.device),
             }
             b["host"] = torch.empty_like(b["out"], device="cpu")
             if self.device.type == "cuda":
@@ -199,24 +210,67 @@ class ShardedSearcher:
         ids = h[:B * k].reshape(B, k).copy()
         scores = h[B * k:2 * B * k].view(np.float64).reshape(B, k).copy()
         cnt = h[2 * B * k:].view(np.int32)
-        return ids, scores, cnt[:B].copy(), int(cnt[B])
+        amb = -1 if cnt[B + 1] != 0 else int(cnt[B])      # the latch: some block of some fuse gave up on a peer
+        return ids, scores, cnt[:B].copy(), amb
 
     def search(self, mode, top_k, q_bits=None, sp_indptr=None, sp_terms=None, sp_weights=None, mask_ids=None,
                score_threshold=None, rrf_k=0, max_retries=4):
-        """Whole sharded path with HOST buffers (query replicated on every rank).  Returns (ids, scores, counts)."""
+        """Whole sharded path with HOST buffers (query replicated on every rank).  Returns (ids, scores, counts).
+
+        Exactness: when some shard's slack guard flags the result, every rank widens its slack and repeats (the
+        ambiguity counter is global, so all ranks take the same decision); after `max_retries` the legs are recomputed
+        EXHAUSTIVELY (always exact) -- or, with B200RAG_EXACT_FALLBACK=0, the search raises instead of returning a
+        result that could differ from the exact top-k."""
+        if self.broken:
+            raise RuntimeError(f"sharded search: {self.broken}; call reset() on every rank")
         nlegs, B, L, k = self.stage(mode, top_k, q_bits, sp_indptr, sp_terms, sp_weights, mask_ids, score_threshold,
                                     rrf_k)
         slack0 = None
-        for attempt in range(max_retries + 1):
-            ids, scores, counts, amb = self.fetch(self.run_staged())
-            if amb < 0:
-                raise RuntimeError("sharded search: a peer's candidates never arrived (exchange flag timed out)")
-            if amb == 0 or attempt == max_retries:
-                break
-            # some shard's slack guard failed: widen on every rank (same decision everywhere: amb is global)
-            slack0 = max(16, L // 2) if slack0 is None else slack0
-            slack0 = slack0 * 2 + L
-            self.shard.set_slack(min(slack0, 3 * 256 - L))
-        if slack0 is not None:
-            self.shard.set_slack(0)
+        exhaustive = False
+        try:
+            for attempt in range(max_retries + 2):
+                ids, scores, counts, amb = self.fetch(self.run_staged())
+                if amb < 0:
+                    self.broken = "a peer's candidates never arrived (exchange flag timed out)"
+                    raise RuntimeError(f"sharded search: {self.broken}")
+                if amb == 0:
+                    break
+                if exhaustive:
+                    raise RuntimeError("sharded search: the exhaustive pass reported ambiguity (internal error)")
+                if attempt >= max_retries:
+                    if not self.exact_fallback:
+                        raise RuntimeError("sharded search: the slack guard never cleared (ties or near-duplicate "
+                                           "scores around the top-k cut) and the exhaustive exact pass is disabled")
+                    exhaustive = True
+                    self.shard.set_exhaustive(True)
+                    continue
+                # some shard's slack guard failed: widen on every rank (same decision everywhere: amb is global)
+                slack0 = max(16, L // 2) if slack0 is None else slack0
+                slack0 = slack0 * 2 + L
+                self.shard.set_slack(min(slack0, 3 * 256 - L))
+        finally:
+            if slack0 is not None:
+                self.shard.set_slack(0)
+            if exhaustive:
+                self.shard.set_exhaustive(False)
         return ids, scores, counts
+
+    def reset(self):
+        """Collective: tear the peer windows down and set them up again (after an exchange timeout the ranks' epochs
+        and parities no longer agree).  Every rank must call it."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        if self.p2p:
+            try:
+                self.shard.p2p_close()
+            except Exception:
+                pass
+        self._bufs.clear()
+        self.p2p = False
+        if self.world > 1 and self.device.type == "cuda" and hasattr(self.shard, "p2p_export") and \
+                os.environ.get("B200RAG_P2P", "1") != "0":
+            self._setup_p2p()
+        if self.pipeline and not self.p2p:
+            self.pipeline = False
+            self.shard.p2p_set_stream(0)
+        self.broken = None

@@ -9,11 +9,19 @@ defaults (``collection_name or config.collection_name`` :56-57, ``top_k or confi
 in libb200rag.so; what stays on the host is what is host work in the reference too: the payload store,
 the collection registry and result materialisation (:334-346).
 
-All collections share one global row space (row id = insertion order); a collection, its
-tombstones and an optional ``filter_metadata`` are expressed as one eligibility bitmask per search
-(north star: "the collection filter applied as a bitmask"), applied in BOTH legs.
+All collections share one global row space (row id = insertion order; ids are never reused or
+renumbered); a collection, its tombstones and an optional ``filter_metadata`` are expressed as one
+eligibility bitmask per search (north star: "the collection filter applied as a bitmask"), applied in BOTH
+legs.
 
-Additive API (no reference counterpart): ``search_batch``.
+Several GPUs behind the ONE retriever object the reference builds (pipeline/orchestrator.py:48-74):
+``devices=[0, 1, ...]`` (or the environment variable ``B200RAG_DEVICES=all | 0,1,2``) makes the retriever own
+one shard per entry, all in this process.  ``add()`` routes each batch to a shard together with its global row
+ids, masks are cut per shard, and ``search`` / ``search_batch`` run the legs on every shard and fuse them
+(``b200rag_group_search``); the results are bit-identical to a single shard holding every row.
+
+Additive API (no reference counterpart): ``search_batch``, ``search_batch_arrays``, ``save`` / ``load``,
+``attach_prebuilt``.
 """
 from __future__ import annotations
 
@@ -42,6 +50,7 @@ except Exception:  # reference not importable here
         return cls
 
 _MASK_CACHE = 64
+_PAYLOAD_CHUNK = 65536          # payloads per file in save()
 
 
 def _sorted_sparse(sv, vocab):
@@ -71,70 +80,190 @@ def _match(payload_meta, key, value):
     return got == value
 
 
+class _Grow:
+    """Append-only numpy vector that grows by doubling (row bookkeeping scales with the corpus, not with objects)."""
+
+    def __init__(self, dtype, cap=1024):
+        self._buf = np.zeros(cap, dtype=dtype)
+        self.n = 0
+
+    @property
+    def view(self):
+        return self._buf[:self.n]
+
+    def reserve(self, extra):
+        need = self.n + extra
+        if need > len(self._buf):
+            cap = len(self._buf)
+            while cap < need:
+                cap *= 2
+            grown = np.zeros(cap, dtype=self._buf.dtype)
+            grown[:self.n] = self._buf[:self.n]
+            self._buf = grown
+
+    def append(self, values):
+        values = np.asarray(values, dtype=self._buf.dtype).reshape(-1)
+        self.reserve(len(values))
+        self._buf[self.n:self.n + len(values)] = values
+        self.n += len(values)
+
+    def fill(self, count, value):
+        self.reserve(count)
+        self._buf[self.n:self.n + count] = value
+        self.n += count
+
+    def assign(self, values):
+        values = np.asarray(values, dtype=self._buf.dtype).reshape(-1)
+        self.n = 0
+        self.append(values)
+
+
+class _PayloadStore:
+    """Payload per global row id.  A list, optionally preceded by a LAZY range whose payloads come from a callable
+    (``attach_prebuilt``: a 10M-row synthetic corpus needs no 10M Python dicts)."""
+
+    def __init__(self):
+        self._lazy_n, self._lazy_fn, self._items = 0, None, []
+
+    def __len__(self):
+        return self._lazy_n + len(self._items)
+
+    def __getitem__(self, i):
+        if i < 0 or i >= len(self):
+            raise IndexError(i)
+        if i < self._lazy_n:
+            return self._lazy_fn(int(i))
+        return self._items[i - self._lazy_n]
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def extend(self, payloads):
+        self._items.extend(payloads)
+
+    def set_lazy(self, n, fn):
+        if len(self):
+            raise RetrievalError("lazy payloads can only be attached to an empty store")
+        self._lazy_n, self._lazy_fn = int(n), fn
+
+    def drop(self, ids):
+        """Forget the payloads of physically dropped rows (ids stay allocated: row ids are never reused)."""
+        for i in ids:
+            if i >= self._lazy_n:
+                self._items[int(i) - self._lazy_n] = None
+
+    def clear(self):
+        self._lazy_n, self._lazy_fn, self._items = 0, None, []
+
+
 @_register
 class B200Retriever(BaseRetriever):
-    """Exact dense / sparse / hybrid-RRF retrieval on one B200 shard (or one rank's shard of a sharded corpus)."""
+    """Exact dense / sparse / hybrid-RRF retrieval on one or several B200 shards owned by this process."""
 
     def __init__(self, config: RetrievalConfig, embedding_dim: int = 1024, *, device: int = 0,
-                 vocab: int = 250_002, docs_per_block: int = 0, rrf_k: int = 2, row_base: int = 0):
+                 devices: list[int] | str | None = None, vocab: int = 250_002, docs_per_block: int = 0,
+                 rrf_k: int = 2, row_base: int = 0, compact_dead_fraction: float = 0.25,
+                 device_add_rows: int = 1024):
         self.config = config
         self.embedding_dim = embedding_dim
-        self._device, self._vocab, self._R, self._rrf_k, self._row_base = device, vocab, docs_per_block, rrf_k, row_base
-        self._shard: _ffi.Shard | None = None
+        self._vocab, self._R, self._rrf_k, self._row_base = vocab, docs_per_block, rrf_k, row_base
+        if devices is None:
+            devices = os.environ.get("B200RAG_DEVICES") or None
+        self._devices_spec = devices if devices is not None else [device]
+        self._compact_dead_fraction = float(compact_dead_fraction)
+        self._device_add_rows = int(device_add_rows)
+        self._shards: list | None = None
+        self._group = None
         self._existing_collections: set[str] = set()
         self._hybrid_collections: set[str] = set()
-        # host-side row bookkeeping
-        self._payloads: list[dict] = []
-        self._row_coll = np.zeros(0, dtype=np.int32)   # collection id per row   } views of length len(_payloads) into
-        self._alive = np.zeros(0, dtype=bool)          # tombstones              } buffers that grow by doubling
-        self._row_cap = (np.zeros(1024, dtype=np.int32), np.zeros(1024, dtype=bool))
+        self._reset_rows()
         self._coll_ids: dict[str, int] = {}
         self._coll_rows: dict[str, int] = {}    # live rows per collection
         self._coll_version: dict[str, int] = {}
-        self._masks: OrderedDict = OrderedDict()  # (collection, filter key) -> (mask_id, version)
-        self._meta_index: dict = {}               # metadata key -> {"upto": rows indexed, "map": value -> [rows], "slow": [rows]}
-        self._next_mask = 0
         logger.info(f"B200Retriever initialized: collection={config.collection_name}, "
                     f"search_type={config.search_type}")
 
-    # ------------------------------------------------------------------ engine handle (qdrant.py:35-54)
-    def _get_shard(self) -> _ffi.Shard:
-        if self._shard is not None:
-            return self._shard
+    def _reset_rows(self):
+        """Empty host-side row bookkeeping (fresh retriever, last collection deleted, load)."""
+        self._payloads = _PayloadStore()
+        self._coll_of = _Grow(np.int32)         # collection id per global row id
+        self._alive_of = _Grow(bool)            # tombstones
+        self._shard_rows: list[_Grow] = []      # per shard: global ids of its local rows, in local order
+        self._stored = 0                        # rows physically held by the shards (live or tombstoned)
+        self._masks: OrderedDict = OrderedDict()  # (collection, filter key) -> (mask_id, version)
+        self._meta_index: dict = {}               # metadata key -> {"upto": ids indexed, "map": value -> [ids], "slow": [ids]}
+        self._next_mask = 0
+        self._layout_epoch = 0                  # bumped when local rows move (compaction): every cached mask is void
+
+    # views used by the tests and by callers that want to look at the row state
+    @property
+    def _row_coll(self):
+        return self._coll_of.view
+
+    @property
+    def _alive(self):
+        return self._alive_of.view
+
+    # ------------------------------------------------------------------ engine handles (qdrant.py:35-54)
+    def _resolve_devices(self) -> list[int]:
+        spec = self._devices_spec
+        if isinstance(spec, str):
+            if spec.strip().lower() == "all":
+                n = _ffi.device_count()
+                if n < 1:
+                    raise RetrievalError("B200RAG_DEVICES=all but no sm_100 device is visible")
+                return list(range(n))
+            return [int(x) for x in spec.replace(" ", "").split(",") if x != ""]
+        return [int(x) for x in spec]
+
+    def _get_shards(self) -> list:
+        if self._shards is not None:
+            return self._shards
         try:
-            self._shard = _ffi.Shard(dim=self.embedding_dim, vocab=self._vocab, device=self._device,
-                                     row_base=self._row_base, docs_per_block=self._R)
-            return self._shard
+            devs = self._resolve_devices()
+            if not devs:
+                raise RetrievalError("no device given")
+            shards = [_ffi.Shard(dim=self.embedding_dim, vocab=self._vocab, device=d, row_base=self._row_base,
+                                 docs_per_block=self._R) for d in devs]
+            self._set_shards(shards)
+            return self._shards
         except Exception as e:
             # same wording as the reference so the API layer's "connect" -> 503 mapping keeps working (api/v1/query.py:151-161)
             raise RetrievalError(f"Failed to connect to the B200 retrieval engine: {e}")
 
+    def _set_shards(self, shards, group=None):
+        self._shards = list(shards)
+        while len(self._shard_rows) < len(self._shards):
+            self._shard_rows.append(_Grow(np.int64))
+        if group is None and len(self._shards) > 1:
+            group = _ffi.ShardGroup(self._shards)
+        self._group = group
+
+    # single-shard handle (kept for callers/tests that inject a shard or a test double)
+    @property
+    def _shard(self):
+        return self._shards[0] if self._shards else None
+
+    @_shard.setter
+    def _shard(self, shard):
+        self._set_shards([shard])
+
+    def _get_shard(self):
+        return self._get_shards()[0]
+
+    @property
+    def n_shards(self) -> int:
+        return len(self._get_shards())
+
     def close(self):
-        if self._shard is not None:
-            self._shard.close()
-            self._shard = None
-
-    def _set_rows(self, coll, alive) -> None:
-        """Replace the per-row bookkeeping (load / clear)."""
-        n = len(coll)
-        cap = max(1024, 1 << int(n - 1).bit_length()) if n else 1024
-        self._row_cap = (np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=bool))
-        self._row_cap[0][:n], self._row_cap[1][:n] = coll, alive
-        self._row_coll, self._alive = self._row_cap[0][:n], self._row_cap[1][:n]
-
-    def _append_rows(self, cid: int, n_new: int) -> None:
-        """n_new live rows of collection `cid` at the end of the row space (amortised O(1) per row)."""
-        n = len(self._row_coll)
-        if n + n_new > len(self._row_cap[0]):
-            cap = len(self._row_cap[0])
-            while cap < n + n_new:
-                cap *= 2
-            grown = (np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=bool))
-            grown[0][:n], grown[1][:n] = self._row_coll, self._alive
-            self._row_cap = grown
-        self._row_cap[0][n:n + n_new] = cid
-        self._row_cap[1][n:n + n_new] = True
-        self._row_coll, self._alive = self._row_cap[0][:n + n_new], self._row_cap[1][:n + n_new]
+        if self._group is not None and hasattr(self._group, "close"):
+            self._group.close()
+        self._group = None
+        if self._shards is not None:
+            for s in self._shards:
+                s.close()
+            self._shards = None
 
     def _resolve_collection(self, collection_name: str | None) -> str:
         return collection_name or self.config.collection_name
@@ -164,11 +293,10 @@ class B200Retriever(BaseRetriever):
 
     # ------------------------------------------------------------------ add (qdrant.py:140-225)
     def _prepare_rows(self, chunks, embeddings, is_hybrid):
-        """Host staging of an add(): payloads, unit bf16 rows, doc-major CSR of the sparse parts."""
+        """Host staging of an add(): payloads, raw fp32 rows, doc-major CSR of the sparse parts."""
         dense = np.asarray([e.dense for e in embeddings], dtype=np.float32)
         if dense.ndim != 2 or dense.shape[1] != self.embedding_dim:
             raise RetrievalError(f"dense vectors must have dimension {self.embedding_dim}")
-        bits = _ffi.normalize_bf16(dense)
         indptr = np.zeros(len(chunks) + 1, dtype=np.int64)
         tt, ww = [], []
         for i, emb in enumerate(embeddings):
@@ -183,7 +311,33 @@ class B200Retriever(BaseRetriever):
         weights = np.concatenate(ww) if ww else np.zeros(0, np.float32)
         payloads = [{"text": c.text, "start": c.start, "end": c.end, "speaker": c.speaker,
                      "metadata": c.metadata or {}} for c in chunks]
-        return bits, indptr, terms, weights, payloads
+        return dense, indptr, terms, weights, payloads
+
+    def _route(self, n: int) -> list[tuple[int, int, int]]:
+        """Which shard takes which contiguous slice of an add() batch: small batches go whole to the emptiest shard,
+        bulk batches are cut into one slice per shard (ids stay increasing inside every shard either way)."""
+        ns = len(self._shards)
+        if ns == 1:
+            return [(0, 0, n)]
+        loads = [g.n for g in self._shard_rows]
+        if n < 4096 * ns:
+            return [(int(np.argmin(loads)), 0, n)]
+        # water-fill: after the add every shard should hold about the same number of rows
+        target = (sum(loads) + n) / ns
+        want = np.maximum(0, np.floor(target - np.asarray(loads))).astype(np.int64)
+        short = n - int(want.sum())
+        order = np.argsort(loads, kind="stable")
+        for i in range(abs(short)):
+            want[order[i % ns]] += 1 if short > 0 else -1 if want[order[i % ns]] > 0 else 0
+        while want.sum() != n:                       # (only when the -1 branch skipped an empty slice)
+            j = int(np.argmax(want))
+            want[j] += n - int(want.sum())
+        parts, lo = [], 0
+        for s in range(ns):
+            if want[s] > 0:
+                parts.append((s, lo, lo + int(want[s])))
+                lo += int(want[s])
+        return parts
 
     @timed
     def add(self, chunks: list[AudioChunk], embeddings: list[EmbeddingResult],
@@ -196,13 +350,31 @@ class B200Retriever(BaseRetriever):
         resolved = self._ensure_collection(collection_name, hybrid=has_sparse)
         try:
             is_hybrid = resolved in self._hybrid_collections
-            bits, indptr, terms, weights, payloads = self._prepare_rows(chunks, embeddings, is_hybrid)
-            self._get_shard().add(bits, indptr, terms, weights)
+            dense, indptr, terms, weights, payloads = self._prepare_rows(chunks, embeddings, is_hybrid)
+            shards = self._get_shards()
             cid = self._coll_ids[resolved]
-            self._payloads.extend(payloads)
-            self._append_rows(cid, len(chunks))
-            self._coll_rows[resolved] += len(chunks)
-            self._coll_version[resolved] += 1
+            n = len(chunks)
+            g0 = self._row_base + len(self._payloads)
+            ids = np.arange(g0, g0 + n, dtype=np.int64)
+            # large batches: the GPU normalises + packs the raw fp32 rows (b200rag_add_f32); small ones use the host
+            # routine (bit-equal) and skip the fp32 upload
+            on_device = n >= self._device_add_rows
+            bits = None if on_device else _ffi.normalize_bf16(dense)
+            for si, lo, hi in self._route(n):
+                ip = indptr[lo:hi + 1] - indptr[lo]
+                tt, ww = terms[indptr[lo]:indptr[hi]], weights[indptr[lo]:indptr[hi]]
+                if on_device:
+                    shards[si].add_f32(dense[lo:hi], ip, tt, ww, ids=ids[lo:hi])
+                else:
+                    shards[si].add(bits[lo:hi], ip, tt, ww, ids=ids[lo:hi])
+                # bookkeeping per slice, so a failure on a later shard leaves rows and books consistent
+                self._payloads.extend(payloads[lo:hi])
+                self._coll_of.fill(hi - lo, cid)
+                self._alive_of.fill(hi - lo, True)
+                self._shard_rows[si].append(ids[lo:hi])
+                self._stored += hi - lo
+                self._coll_rows[resolved] += hi - lo
+                self._coll_version[resolved] += 1
             logger.info(f"Added {len(chunks)} chunks to {resolved} (hybrid={is_hybrid})")
         except RetrievalError as e:
             raise RetrievalError(f"Failed to add chunks to '{resolved}': {e}")
@@ -211,48 +383,55 @@ class B200Retriever(BaseRetriever):
 
     # ------------------------------------------------------------------ eligibility masks (R4)
     def _eligible(self, resolved: str, filter_metadata: dict | None) -> np.ndarray | None:
-        """bool[n_rows] or None when every stored row is eligible (single live collection, no filter)."""
+        """bool per global row id, or None when every STORED row is eligible (one live collection, no filter)."""
         n = len(self._payloads)
-        if not filter_metadata and self._coll_rows.get(resolved, 0) == n:
+        if not filter_metadata and self._coll_rows.get(resolved, 0) == self._stored:
             return None
         cid = self._coll_ids[resolved]
         elig = (self._row_coll == cid) & self._alive
         for k, v in (filter_metadata or {}).items():
             hit = np.zeros(n, dtype=bool)
-            hit[self._meta_rows(k, v)] = True
+            hit[self._meta_rows(k, v) - self._row_base] = True
             elig &= hit
         return elig
 
     def _meta_rows(self, key, value) -> np.ndarray:
-        """Rows (of any collection) whose ``metadata[key]`` matches ``value`` under ``_match``.  A per-key payload
-        index (value -> rows, list-valued fields indexed by element) is built on the first filter that names the key
-        and extended as rows are added -- the host-side analogue of a qdrant payload index, so that a new filter costs
-        one lookup instead of a Python pass over every payload."""
+        """Global ids of the rows (of any collection) whose ``metadata[key]`` matches ``value`` under ``_match``.  A
+        per-key payload index (value -> rows, list-valued fields indexed by element) is built on the first filter that
+        names the key and extended as rows are added -- the host-side analogue of a qdrant payload index, so that a
+        new filter costs one lookup instead of a Python pass over every payload."""
         idx = self._meta_index.setdefault(key, {"upto": 0, "map": {}, "slow": []})
+        base = self._row_base
         for r in range(idx["upto"], len(self._payloads)):
-            meta = self._payloads[r].get("metadata")
+            p = self._payloads[r]
+            meta = p.get("metadata") if p is not None else None
             if not isinstance(meta, dict) or key not in meta:
                 continue
             got = meta[key]
             try:
                 for item in (got if isinstance(got, (list, tuple)) else (got,)):
                     rows = idx["map"].setdefault(item, [])
-                    if not rows or rows[-1] != r:
-                        rows.append(r)
+                    if not rows or rows[-1] != r + base:
+                        rows.append(r + base)
             except TypeError:                     # unhashable stored value: matched the slow way
-                idx["slow"].append(r)
+                idx["slow"].append(r + base)
         idx["upto"] = len(self._payloads)
         try:
             rows = list(idx["map"].get(value, ()))
             slow = idx["slow"]
         except TypeError:                         # unhashable filter value: every row that has the key is a candidate
             rows, slow = [], sorted({r for rr in idx["map"].values() for r in rr} | set(idx["slow"]))
-        rows += [r for r in slow if _match(self._payloads[r].get("metadata"), key, value)]
+        for r in slow:
+            p = self._payloads[r - base]
+            if p is not None and _match(p.get("metadata"), key, value):
+                rows.append(r)
         return np.asarray(rows, dtype=np.int64)
 
     def _mask_id(self, resolved: str, filter_metadata: dict | None) -> int:
+        """Mask id (the same on every shard) for (collection, filter), uploading it if it is not cached; -1 = all rows.
+        Nothing is evicted here: `_execute` trims the cache after the search that may still use the ids."""
         elig_key = (resolved, tuple(sorted((str(k), repr(v)) for k, v in (filter_metadata or {}).items())))
-        version = (self._coll_version[resolved], len(self._payloads))
+        version = (self._coll_version[resolved], len(self._payloads), self._layout_epoch)
         hit = self._masks.get(elig_key)
         if hit is not None and hit[1] == version:
             self._masks.move_to_end(elig_key)
@@ -260,19 +439,32 @@ class B200Retriever(BaseRetriever):
         elig = self._eligible(resolved, filter_metadata)
         if elig is None:
             return -1
-        shard = self._get_shard()
+        shards = self._get_shards()
         if hit is not None:
             mid = hit[0]
         else:
             mid = self._next_mask
             self._next_mask += 1
-        shard.mask_set(mid, pack_mask(elig), len(elig))
+        for s, sh in enumerate(shards):
+            local = self._shard_rows[s].view - self._row_base          # global ids of the shard's local rows
+            sh.mask_set(mid, pack_mask(elig[local]), len(local))
         self._masks[elig_key] = (mid, version)
         self._masks.move_to_end(elig_key)
-        while len(self._masks) > _MASK_CACHE:
-            _, (old, _v) = self._masks.popitem(last=False)
-            shard.mask_drop(old)
         return mid
+
+    def _evict_masks(self, pinned: set) -> None:
+        """LRU eviction, never of a mask the batch that just ran was using (its ids were already handed to the engine)."""
+        shards = self._get_shards()
+        limit = max(_MASK_CACHE, len(pinned))
+        for key in list(self._masks):
+            if len(self._masks) <= limit:
+                break
+            mid = self._masks[key][0]
+            if mid in pinned:
+                continue
+            del self._masks[key]
+            for sh in shards:
+                sh.mask_drop(mid)
 
     # ------------------------------------------------------------------ search (qdrant.py:227-352)
     def _plan_search(self, query_embedding, top_k, collection_name, filter_metadata, search_type) -> dict:
@@ -375,23 +567,32 @@ class B200Retriever(BaseRetriever):
         out["materialise"] = lambda b, j: self._materialise(ids[b, j:j + 1], scores[b, j:j + 1], 1, out["sources"][b])[0]
         return out
 
+    def _search_engine(self, mode, k, q_bits, indptr, terms, weights, mask_ids, thr):
+        """One engine call for a homogeneous batch: the single shard, or the group over all shards."""
+        target = self._shards[0] if len(self._shards) == 1 else self._group
+        return target.search(mode, k, q_bits, indptr, terms, weights, mask_ids=mask_ids, score_threshold=thr,
+                             rrf_k=self._rrf_k)
+
     def _execute(self, embeddings, plans, raw: bool = False) -> list:
         results: list = [None] * len(plans)
         groups: dict = {}
         for i, p in enumerate(plans):
             if self._coll_rows.get(p["collection"], 0) == 0:
                 # the engine is still required to exist: a missing GPU/library must not look like "no results"
-                self._get_shard()
+                self._get_shards()
                 results[i] = (np.zeros(0, np.int64), np.zeros(0, np.float64), 0) if raw else []
                 continue
             groups.setdefault((p["mode"], p["top_k"], p["score_threshold"]), []).append(i)
         for (mode, k, thr), idxs in groups.items():
-            shard = self._get_shard()
+            self._get_shards()
             q_bits, indptr, terms, weights = self._query_arrays([embeddings[i] for i in idxs], mode)
             mask_ids = np.asarray([self._mask_id(plans[i]["collection"], plans[i]["filter"]) for i in idxs], np.int32)
-            ids, scores, counts = shard.search(mode, k, q_bits, indptr, terms, weights,
-                                               mask_ids=mask_ids if (mask_ids >= 0).any() else None,
-                                               score_threshold=thr, rrf_k=self._rrf_k)
+            try:
+                ids, scores, counts = self._search_engine(mode, k, q_bits, indptr, terms, weights,
+                                                          mask_ids if (mask_ids >= 0).any() else None, thr)
+            finally:
+                if len(self._masks) > _MASK_CACHE:
+                    self._evict_masks({int(m) for m in mask_ids if m >= 0})
             for j, i in enumerate(idxs):
                 results[i] = (ids[j], scores[j], int(counts[j])) if raw else \
                     self._materialise(ids[j], scores[j], counts[j], plans[i]["collection"])
@@ -399,6 +600,9 @@ class B200Retriever(BaseRetriever):
 
     # ------------------------------------------------------------------ admin (qdrant.py:354-381)
     def delete_collection(self, collection_name: str | None = None) -> None:
+        """qdrant.py:354-363 drops the collection's storage.  Here the rows are tombstoned through the masks at once and
+        PHYSICALLY dropped (dense rows, forward and inverted index, on the device) as soon as a shard's dead fraction
+        exceeds ``compact_dead_fraction``; when nothing is live anywhere everything is dropped."""
         resolved = self._resolve_collection(collection_name)
         try:
             if resolved in self._existing_collections:
@@ -408,66 +612,174 @@ class B200Retriever(BaseRetriever):
                 self._coll_version[resolved] += 1
                 if not self._alive.any():
                     # nothing live anywhere: drop the rows for real
-                    if self._shard is not None:
-                        self._shard.clear()
-                    self._payloads.clear()
-                    self._set_rows([], [])
-                    self._masks.clear()
-                    self._meta_index.clear()
+                    if self._shards is not None:
+                        for s in self._shards:
+                            s.clear()
+                    n_shards = len(self._shard_rows)
+                    self._reset_rows()
+                    self._shard_rows = [_Grow(np.int64) for _ in range(n_shards)]
+                else:
+                    self._compact()
             self._existing_collections.discard(resolved)
             self._hybrid_collections.discard(resolved)
             logger.info(f"Deleted collection: {resolved}")
         except Exception as e:
             raise RetrievalError(f"Failed to delete collection '{resolved}': {e}")
 
+    def _compact(self, force: bool = False) -> int:
+        """Physically drop tombstoned rows on every shard whose dead fraction exceeds the threshold; returns the
+        number of rows dropped.  Global ids do not change (the shards keep their id maps), only local positions do,
+        so every cached mask is invalidated."""
+        if self._shards is None:
+            return 0
+        dropped = 0
+        base = self._row_base
+        for s, sh in enumerate(self._shards):
+            rows = self._shard_rows[s].view
+            if len(rows) == 0:
+                continue
+            keep = self._alive[rows - base]
+            dead = int(len(rows) - keep.sum())
+            if dead == 0 or (not force and dead <= self._compact_dead_fraction * len(rows)):
+                continue
+            sh.compact(pack_mask(keep), len(rows))
+            self._payloads.drop(rows[~keep] - base)
+            self._shard_rows[s].assign(rows[keep])
+            self._stored -= dead
+            dropped += dead
+        if dropped:
+            self._layout_epoch += 1
+            self._masks.clear()           # (the engine dropped its masks with the rows)
+            logger.info(f"Compacted {dropped} deleted rows")
+        return dropped
+
+    # ------------------------------------------------------------------ bulk attach (additive; bench / offline builds)
+    def attach_prebuilt(self, shards, collection_name: str | None = None, *, payload_fn=None, hybrid: bool = True,
+                        group=None) -> None:
+        """Adopt shards that were filled OUTSIDE the plugin (bulk / synthetic ingest straight into device memory):
+        their rows become ONE collection of this (empty) retriever.  Every shard must hold the contiguous id range
+        [row_base_s, row_base_s + count_s), the ranges back to back from this retriever's ``row_base``.
+        ``payload_fn(global_id) -> payload dict`` supplies payloads on demand (no per-row Python objects are kept)."""
+        if len(self._payloads) or self._shards is not None:
+            raise RetrievalError("attach_prebuilt() needs an empty retriever")
+        resolved = self._ensure_collection(collection_name, hybrid=hybrid)
+        self._set_shards(shards, group)
+        lo = self._row_base
+        for s, sh in enumerate(self._shards):
+            n = int(sh.count)
+            if int(sh.row_base) != lo:
+                raise RetrievalError("attach_prebuilt: shard id ranges must be contiguous from row_base")
+            self._shard_rows[s].assign(np.arange(lo, lo + n, dtype=np.int64))
+            lo += n
+        total = lo - self._row_base
+        fn = payload_fn or (lambda i: {"text": f"row {i}", "start": 0.0, "end": 0.0, "speaker": None, "metadata": {}})
+        base = self._row_base
+        self._payloads.set_lazy(total, lambda i: fn(i + base))
+        self._coll_of.fill(total, self._coll_ids[resolved])
+        self._alive_of.fill(total, True)
+        self._stored = total
+        self._coll_rows[resolved] = total
+        self._coll_version[resolved] += 1
+
     # ------------------------------------------------------------------ persistence (additive; SURVEY 8f rank 2)
-    # The reference keeps its index in Qdrant's volume (docker-compose.yml:36-37).  Here a retriever is three files:
-    #   shard.bin       rows + forward sparse index (b200rag_save; the inverted index is rebuilt on load)
-    #   payloads.jsonl  one payload per row, insertion order (row id = line number, rule R1)
-    #   manifest.json   collections (ids, hybrid flags, live counts), row -> collection, tombstones, geometry
+    # The reference keeps its index in Qdrant's volume (docker-compose.yml:36-37).  Here a retriever is a directory:
+    #   shard-<i>.bin        rows + forward sparse index + global row ids of shard i (b200rag_save; the inverted index
+    #                        is rebuilt on load)
+    #   payloads-<j>.json    payloads of global ids [j * 65536, (j + 1) * 65536) as ONE JSON array (null = dropped row)
+    #   rows.npz             per global id: collection id, tombstone; per shard: the global ids of its local rows
+    #   manifest.json        format, geometry, collections (written LAST: a directory without it is not a snapshot)
+    # Every file is written under a temporary name and renamed into place.
     def save(self, directory: str) -> None:
         try:
             os.makedirs(directory, exist_ok=True)
-            self._get_shard().save(os.path.join(directory, "shard.bin"))
-            with open(os.path.join(directory, "payloads.jsonl"), "w", encoding="utf-8") as f:
-                for p in self._payloads:
-                    f.write(json.dumps(p, ensure_ascii=False) + "\n")
+            shards = self._get_shards()
+
+            def put(name, writer):
+                tmp = os.path.join(directory, f".{name}.tmp-{os.getpid()}")
+                writer(tmp)
+                os.replace(tmp, os.path.join(directory, name))
+
+            for i, sh in enumerate(shards):
+                put(f"shard-{i}.bin", sh.save)
+            n = len(self._payloads)
+            n_chunks = (n + _PAYLOAD_CHUNK - 1) // _PAYLOAD_CHUNK
+            for j in range(n_chunks):
+                block = [self._payloads[i] for i in range(j * _PAYLOAD_CHUNK, min(n, (j + 1) * _PAYLOAD_CHUNK))]
+
+                def w(tmp, block=block):
+                    with open(tmp, "w", encoding="utf-8") as f:
+                        json.dump(block, f, ensure_ascii=False)
+                put(f"payloads-{j}.json", w)
+
+            def wrows(tmp):
+                with open(tmp, "wb") as f:
+                    np.savez(f, row_collection=self._row_coll, alive=self._alive,
+                             **{f"shard_rows_{i}": g.view for i, g in enumerate(self._shard_rows)})
+            put("rows.npz", wrows)
             manifest = {
-                "format": "b200rag-retriever-1", "embedding_dim": self.embedding_dim, "vocab": self._vocab,
-                "row_base": self._row_base, "rows": len(self._payloads),
+                "format": "b200rag-retriever-2", "embedding_dim": self.embedding_dim, "vocab": self._vocab,
+                "row_base": self._row_base, "rows": n, "shards": len(shards), "payload_chunks": n_chunks,
+                "payload_chunk_rows": _PAYLOAD_CHUNK,
                 "collections": {name: {"id": cid, "hybrid": name in self._hybrid_collections,
                                        "exists": name in self._existing_collections,
                                        "live_rows": self._coll_rows.get(name, 0)}
                                 for name, cid in self._coll_ids.items()},
-                "row_collection": self._row_coll.tolist(), "alive": self._alive.astype(int).tolist(),
             }
-            with open(os.path.join(directory, "manifest.json"), "w", encoding="utf-8") as f:
-                json.dump(manifest, f)
+
+            def wman(tmp):
+                with open(tmp, "w", encoding="utf-8") as f:
+                    json.dump(manifest, f)
+            put("manifest.json", wman)
         except Exception as e:
             raise RetrievalError(f"Failed to save retriever to '{directory}': {e}")
 
     def load(self, directory: str) -> None:
-        """Restore a saved retriever into this (empty) one; config/embedding_dim/vocab must match the saved ones."""
+        """Restore a saved retriever into this one, which must hold no rows; its collection registry is REPLACED by the
+        saved one (names registered earlier, e.g. by a ``count()`` health probe, do not survive).  embedding_dim,
+        vocab and the number of shards must match the saved ones."""
         try:
-            if self._payloads:
-                raise RetrievalError("load() needs an empty retriever")
+            if len(self._payloads) or self._stored:
+                raise RetrievalError("load() needs a retriever without rows")
             with open(os.path.join(directory, "manifest.json"), encoding="utf-8") as f:
                 m = json.load(f)
-            if m.get("format") != "b200rag-retriever-1" or m["embedding_dim"] != self.embedding_dim or \
+            if m.get("format") != "b200rag-retriever-2" or m["embedding_dim"] != self.embedding_dim or \
                     m["vocab"] != self._vocab:
                 raise RetrievalError("manifest does not match this retriever (format, embedding_dim or vocab)")
-            with open(os.path.join(directory, "payloads.jsonl"), encoding="utf-8") as f:
-                payloads = [json.loads(line) for line in f]
-            if len(payloads) != m["rows"] or len(m["row_collection"]) != m["rows"] or len(m["alive"]) != m["rows"]:
-                raise RetrievalError("payloads.jsonl / manifest.json row counts disagree")
-            shard = self._get_shard()
-            shard.load(os.path.join(directory, "shard.bin"))
-            if shard.count != m["rows"]:
-                shard.clear()
-                raise RetrievalError("shard.bin holds a different number of rows than the manifest")
+            shards = self._get_shards()
+            if m["shards"] != len(shards):
+                raise RetrievalError(f"snapshot has {m['shards']} shards, this retriever has {len(shards)}")
+            payloads: list = []
+            for j in range(m["payload_chunks"]):
+                with open(os.path.join(directory, f"payloads-{j}.json"), encoding="utf-8") as f:
+                    payloads.extend(json.load(f))
+            z = np.load(os.path.join(directory, "rows.npz"), allow_pickle=False)
+            row_coll, alive = z["row_collection"], z["alive"]
+            if len(payloads) != m["rows"] or len(row_coll) != m["rows"] or len(alive) != m["rows"]:
+                raise RetrievalError("payload files / rows.npz / manifest.json row counts disagree")
+            shard_rows = [z[f"shard_rows_{i}"] for i in range(len(shards))]
+            try:
+                for i, sh in enumerate(shards):
+                    sh.load(os.path.join(directory, f"shard-{i}.bin"))
+                    if sh.count != len(shard_rows[i]):
+                        raise RetrievalError(f"shard-{i}.bin holds a different number of rows than rows.npz")
+            except Exception:
+                for sh in shards:
+                    sh.clear()
+                raise
+            # everything was read and checked: replace the registry and the row books in one go
+            self._reset_rows()
             self._row_base = m["row_base"]
-            self._payloads = payloads
-            self._set_rows(np.asarray(m["row_collection"], dtype=np.int32), np.asarray(m["alive"], dtype=bool))
+            self._payloads.extend(payloads)
+            self._coll_of.assign(row_coll)
+            self._alive_of.assign(alive)
+            self._shard_rows = []
+            for rows in shard_rows:
+                g = _Grow(np.int64)
+                g.assign(rows)
+                self._shard_rows.append(g)
+            self._stored = int(sum(len(r) for r in shard_rows))
+            self._coll_ids, self._coll_rows = {}, {}
+            self._existing_collections, self._hybrid_collections = set(), set()
             for name, c in m["collections"].items():
                 self._coll_ids[name] = int(c["id"])
                 self._coll_rows[name] = int(c["live_rows"])
@@ -476,8 +788,6 @@ class B200Retriever(BaseRetriever):
                     self._existing_collections.add(name)
                 if c["hybrid"]:
                     self._hybrid_collections.add(name)
-            self._masks.clear()
-            self._meta_index.clear()
         except RetrievalError as e:
             raise RetrievalError(f"Failed to load retriever from '{directory}': {e}")
         except Exception as e:

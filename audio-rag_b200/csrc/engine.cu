@@ -114,16 +114,33 @@ static int ensure_pinned(Shard* s, size_t bytes) {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// ids_host: global ids of the new rows (strictly increasing, above every id stored so far) or nullptr = row_base + local
 static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
-                       const float* w, int64_t nnz, bool host) {
+                       const float* w, int64_t nnz, bool host, const int64_t* ids_host, int dense_on_device = -1) {
     cudaStream_t st = s->stream;
-    const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;   // CSR arrays
+    const cudaMemcpyKind dkind = (dense_on_device < 0 ? !host : dense_on_device != 0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const size_t row_bytes = (size_t)s->dim * 2;
+    int64_t new_last;
+    if (ids_host != nullptr) {
+        int64_t prev = s->last_id;
+        for (int64_t i = 0; i < n; ++i) {
+            if (ids_host[i] <= prev) { set_error("add: row ids must be strictly increasing over the shard's lifetime"); return B200RAG_ERR_INVALID; }
+            prev = ids_host[i];
+        }
+        new_last = prev;
+    } else {
+        if (s->cfg.row_base + s->n_rows <= s->last_id) { set_error("add: implicit row id (row_base + local row) is not above the ids stored so far"); return B200RAG_ERR_INVALID; }
+        new_last = s->cfg.row_base + s->n_rows + n - 1;
+    }
+    B2_TRY(s->row_ids.ensure((size_t)(s->n_rows + n) * 8, (size_t)s->n_rows * 8, st));
+    if (ids_host != nullptr) B2_CUDA(cudaMemcpyAsync(s->row_ids.as<int64_t>() + s->n_rows, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    else B2_TRY(launch_fill_row_ids(s, s->row_ids.as<int64_t>() + s->n_rows, s->cfg.row_base + s->n_rows, n));
     B2_TRY(s->dense.ensure((size_t)(s->n_rows + n) * row_bytes, (size_t)s->n_rows * row_bytes, st));
     B2_TRY(s->fwd_ptr.ensure((size_t)(s->n_rows + n + 1) * 8, (size_t)(s->n_rows + 1) * 8, st));
     B2_TRY(s->fwd_terms.ensure((size_t)(s->nnz + nnz + 1) * 4, (size_t)s->nnz * 4, st));
     B2_TRY(s->fwd_w.ensure((size_t)(s->nnz + nnz + 1) * 4, (size_t)s->nnz * 4, st));
-    B2_CUDA(cudaMemcpyAsync(s->dense.as<uint8_t>() + (size_t)s->n_rows * row_bytes, dense, (size_t)n * row_bytes, kind, st));
+    B2_CUDA(cudaMemcpyAsync(s->dense.as<uint8_t>() + (size_t)s->n_rows * row_bytes, dense, (size_t)n * row_bytes, dkind, st));
     int64_t* fp = s->fwd_ptr.as<int64_t>() + s->n_rows;  // fp[0] already holds s->nnz
     if (indptr == nullptr) {
         std::vector<int64_t> flat((size_t)n, s->nnz);
@@ -149,6 +166,7 @@ static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t
     }
     s->n_rows += n;
     s->nnz += nnz;
+    s->last_id = new_last;
     return B200RAG_OK;
 }
 
@@ -171,6 +189,21 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
 
     const bool want_dense = q.mode != B200RAG_SPARSE;
     const bool want_sparse = q.mode != B200RAG_DENSE;
+    if (s->exhaustive) {
+        // always-exact path: canonical score of every eligible row + full sort, no scan kernels, never ambiguous
+        s->stats.exhaustive = 1;
+        b200rag_cand* o = cands;
+        if (want_dense) {
+            if (s->n_rows == 0) B2_CUDA(cudaMemsetAsync(o, 0, (size_t)B * L * sizeof(b200rag_cand), st));
+            else B2_TRY(launch_exhaustive_leg(s, false, B, L, q.has_threshold && q.mode == B200RAG_DENSE, q.score_threshold, o));
+            o += (size_t)B * L;
+        }
+        if (want_sparse) {
+            if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) B2_CUDA(cudaMemsetAsync(o, 0, (size_t)B * L * sizeof(b200rag_cand), st));
+            else B2_TRY(launch_exhaustive_leg(s, true, B, L, 0, 0.f, o));
+        }
+        return B200RAG_OK;
+    }
     if (want_sparse && s->built_rows != s->n_rows) B2_TRY(build_inverted(s));
 
     // Hybrid: the sparse leg (scan + fused tail) runs on the side stream while the dense scan streams the corpus.
@@ -267,6 +300,26 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         B2_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     }
     (void)nlegs;
+    return B200RAG_OK;
+}
+
+// host-side validation of a doc-major CSR handed to add (indptr from 0 and monotone, terms ascending/unique/in range)
+static int validate_csr_host(const Shard* s, int64_t n, const int64_t* indptr, const uint32_t* terms, const float* w,
+                             int64_t* nnz_out) {
+    *nnz_out = 0;
+    if (indptr == nullptr) return B200RAG_OK;
+    if (indptr[0] != 0) { set_error("add: sparse indptr must start at 0"); return B200RAG_ERR_INVALID; }
+    const int64_t nnz = indptr[n];
+    if (nnz > 0 && (terms == nullptr || w == nullptr)) { set_error("add: sparse terms/weights missing"); return B200RAG_ERR_INVALID; }
+    for (int64_t d = 0; d < n; ++d) {
+        if (indptr[d + 1] < indptr[d]) { set_error("add: sparse indptr not monotone"); return B200RAG_ERR_INVALID; }
+        for (int64_t i = indptr[d]; i < indptr[d + 1]; ++i) {
+            if (terms[i] >= (uint32_t)s->vocab) { set_error("add: sparse index out of vocabulary range"); return B200RAG_ERR_INVALID; }
+            if (i > indptr[d] && terms[i] <= terms[i - 1]) { set_error("add: sparse indices must be ascending and unique per row"); return B200RAG_ERR_INVALID; }
+            if (!isfinite(w[i])) { set_error("add: non-finite sparse weight"); return B200RAG_ERR_INVALID; }
+        }
+    }
+    *nnz_out = nnz;
     return B200RAG_OK;
 }
 
@@ -386,6 +439,8 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_OVERLAP_GEMM")) s->overlap_gemm = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
+    if (const char* e = getenv("B200RAG_EXACT_FALLBACK")) s->exact_fallback = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_P2P_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms > 0) s->x_timeout_cycles = ms * 2000000ll; }
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }
     int rc = s->fwd_ptr.ensure((size_t)(std::max<int64_t>(cfg->reserve_rows, 1024) + 1) * 8, 0, s->stream);
     if (rc == B200RAG_OK) {
@@ -408,7 +463,8 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     cudaSetDevice(s->cfg.device);
     cudaStreamSynchronize(s->stream);
     p2p_release(s);
-    s->dense.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
+    s->dense.release(); s->row_ids.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
+    s->ws.ex_keys.release(); s->ws.ex_sorted.release(); s->ws.ex_temp.release();
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
     for (auto& sl : s->slots) sl.buf.release();
@@ -440,6 +496,20 @@ int b200rag_set_slack(b200rag_shard* sp, int32_t slack) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || slack < 0) { set_error("set_slack: bad argument"); return B200RAG_ERR_INVALID; }
     s->slack = slack;
+    return B200RAG_OK;
+}
+
+int b200rag_set_exhaustive(b200rag_shard* sp, int32_t on) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    s->exhaustive = on != 0;
+    return B200RAG_OK;
+}
+
+int b200rag_set_exact_fallback(b200rag_shard* sp, int32_t on) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    s->exact_fallback = on != 0;
     return B200RAG_OK;
 }
 
@@ -477,37 +547,82 @@ int b200rag_sync(b200rag_shard* sp) {
 
 int b200rag_add(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
                 const float* w) {
+    return b200rag_add_ids(sp, n, dense, indptr, terms, w, nullptr);
+}
+
+int b200rag_add_ids(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
+                    const float* w, const int64_t* ids) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || n < 0 || (n > 0 && dense == nullptr)) { set_error("add: bad argument"); return B200RAG_ERR_INVALID; }
     if (n == 0) return B200RAG_OK;
     if (s->n_rows + n > 0xFFFFFFF0ll) { set_error("add: shard row limit (2^32) exceeded"); return B200RAG_ERR_INVALID; }
     int64_t nnz = 0;
-    if (indptr != nullptr) {
-        if (indptr[0] != 0) { set_error("add: sparse indptr must start at 0"); return B200RAG_ERR_INVALID; }
-        nnz = indptr[n];
-        if (nnz > 0 && (terms == nullptr || w == nullptr)) { set_error("add: sparse terms/weights missing"); return B200RAG_ERR_INVALID; }
-        for (int64_t d = 0; d < n; ++d) {
-            if (indptr[d + 1] < indptr[d]) { set_error("add: sparse indptr not monotone"); return B200RAG_ERR_INVALID; }
-            for (int64_t i = indptr[d]; i < indptr[d + 1]; ++i) {
-                if (terms[i] >= (uint32_t)s->vocab) { set_error("add: sparse index out of vocabulary range"); return B200RAG_ERR_INVALID; }
-                if (i > indptr[d] && terms[i] <= terms[i - 1]) { set_error("add: sparse indices must be ascending and unique per row"); return B200RAG_ERR_INVALID; }
-                if (!isfinite(w[i])) { set_error("add: non-finite sparse weight"); return B200RAG_ERR_INVALID; }
-            }
-        }
-    }
+    B2_TRY(validate_csr_host(s, n, indptr, terms, w, &nnz));
     B2_TRY(use_device(s));
-    return append_rows(s, n, dense, indptr, terms, w, nnz, true);
+    return append_rows(s, n, dense, indptr, terms, w, nnz, true, ids);
+}
+
+int b200rag_add_f32(b200rag_shard* sp, int64_t n, const float* dense_f32, const int64_t* indptr, const uint32_t* terms,
+                    const float* w, const int64_t* ids) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || n < 0 || (n > 0 && dense_f32 == nullptr)) { set_error("add_f32: bad argument"); return B200RAG_ERR_INVALID; }
+    if (n == 0) return B200RAG_OK;
+    if (s->n_rows + n > 0xFFFFFFF0ll) { set_error("add_f32: shard row limit (2^32) exceeded"); return B200RAG_ERR_INVALID; }
+    int64_t nnz = 0;
+    B2_TRY(validate_csr_host(s, n, indptr, terms, w, &nnz));
+    B2_TRY(use_device(s));
+    // raw fp32 rows -> device -> unit bf16 rows (the device twin of b200rag_normalize_bf16), in slices of <= 64k rows
+    DevBuf xf, xb;
+    const int64_t slice = 65536;
+    int rc = xf.ensure((size_t)std::min(n, slice) * s->dim * 4, 0, s->stream);
+    if (rc == B200RAG_OK) rc = xb.ensure((size_t)n * s->dim * 2, 0, s->stream);
+    for (int64_t r0 = 0; r0 < n && rc == B200RAG_OK; r0 += slice) {
+        const int64_t m = std::min(slice, n - r0);
+        cudaError_t e = cudaMemcpyAsync(xf.p, dense_f32 + (size_t)r0 * s->dim, (size_t)m * s->dim * 4, cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(add_f32)"); break; }
+        rc = b200rag_normalize_bf16_device(sp, xf.as<float>(), m, xb.as<uint16_t>() + (size_t)r0 * s->dim);
+    }
+    if (rc == B200RAG_OK) rc = append_rows(s, n, xb.as<uint16_t>(), indptr, terms, w, nnz, true, ids, 1);
+    xf.release(); xb.release();
+    return rc;
 }
 
 int b200rag_add_device(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr,
                        const uint32_t* terms, const float* w, int64_t nnz) {
+    return b200rag_add_device_ids(sp, n, dense, indptr, terms, w, nnz, nullptr);
+}
+
+int b200rag_add_device_ids(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr,
+                           const uint32_t* terms, const float* w, int64_t nnz, const int64_t* ids) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || n < 0 || nnz < 0 || (n > 0 && dense == nullptr)) { set_error("add_device: bad argument"); return B200RAG_ERR_INVALID; }
     if (n == 0) return B200RAG_OK;
     if (s->n_rows + n > 0xFFFFFFF0ll) { set_error("add_device: shard row limit (2^32) exceeded"); return B200RAG_ERR_INVALID; }
     if (indptr == nullptr) nnz = 0;
     B2_TRY(use_device(s));
-    return append_rows(s, n, dense, indptr, terms, w, nnz, false);
+    return append_rows(s, n, dense, indptr, terms, w, nnz, false, ids);
+}
+
+int b200rag_compact(b200rag_shard* sp, const uint32_t* keep_words, int64_t n_rows_mask) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || keep_words == nullptr) { set_error("compact: null argument"); return B200RAG_ERR_INVALID; }
+    if (n_rows_mask != s->n_rows) { set_error("compact: the keep mask must cover exactly the shard's rows"); return B200RAG_ERR_INVALID; }
+    if (s->n_rows == 0) return B200RAG_OK;
+    B2_TRY(use_device(s));
+    const size_t words = (size_t)((s->n_rows + 31) / 32);
+    DevBuf km;
+    B2_TRY(km.ensure(words * 4, 0, s->stream));
+    cudaError_t e = cudaMemcpyAsync(km.p, keep_words, words * 4, cudaMemcpyHostToDevice, s->stream);
+    if (e != cudaSuccess) { km.release(); return cuda_fail(e, "cudaMemcpyAsync(keep mask)"); }
+    const int rc = compact_rows(s, km.as<uint32_t>());
+    km.release();
+    if (rc != B200RAG_OK) return rc;
+    // local rows moved: masks and staged batches (which hold local bit positions / raw mask pointers) are void
+    for (auto& kv : s->masks) kv.second.release();
+    s->masks.clear(); s->mask_rows.clear();
+    s->staged = false;
+    for (auto& sl : s->slots) sl.staged = false;
+    return B200RAG_OK;
 }
 
 int b200rag_build(b200rag_shard* sp) {
@@ -527,6 +642,9 @@ int b200rag_clear(b200rag_shard* sp) {
     B2_CUDA(cudaStreamSynchronize(s->stream));
     s->n_rows = 0; s->nnz = 0; s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0;
     s->w_absmax = 0.f; s->wmax_nnz = 0;
+    s->last_id = INT64_MIN;
+    B2_CUDA(cudaMemsetAsync(s->fwd_ptr.p, 0, 8, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
     s->h_blk_base.clear();
     s->staged = false;
     for (auto& sl : s->slots) sl.staged = false;
@@ -541,6 +659,37 @@ int b200rag_read_dense(b200rag_shard* sp, int64_t row, int64_t n, uint16_t* out)
     B2_TRY(use_device(s));
     B2_CUDA(cudaMemcpyAsync(out, s->dense.as<uint16_t>() + (size_t)row * s->dim, (size_t)n * s->dim * 2, cudaMemcpyDeviceToHost, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B200RAG_OK;
+}
+
+int b200rag_read_sparse(b200rag_shard* sp, int64_t row, int64_t n, int64_t* indptr_out, uint32_t* terms_out,
+                        float* weights_out, int64_t cap_nnz) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || row < 0 || n < 0 || row + n > s->n_rows || indptr_out == nullptr) { set_error("read_sparse: bad range"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_CUDA(cudaMemcpyAsync(indptr_out, s->fwd_ptr.as<int64_t>() + row, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    const int64_t base = indptr_out[0];
+    for (int64_t i = 0; i <= n; ++i) indptr_out[i] -= base;
+    const int64_t nnz = indptr_out[n];
+    if (terms_out == nullptr || weights_out == nullptr) return B200RAG_OK;
+    if (cap_nnz < nnz) { set_error("read_sparse: output arrays are smaller than the rows' postings"); return B200RAG_ERR_INVALID; }
+    if (nnz > 0) {
+        B2_CUDA(cudaMemcpyAsync(terms_out, s->fwd_terms.as<uint32_t>() + base, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaMemcpyAsync(weights_out, s->fwd_w.as<float>() + base, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return B200RAG_OK;
+}
+
+int b200rag_read_row_ids(b200rag_shard* sp, int64_t row, int64_t n, int64_t* out) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr || row < 0 || n < 0 || row + n > s->n_rows || out == nullptr) { set_error("read_row_ids: bad range"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    if (n > 0) {
+        B2_CUDA(cudaMemcpyAsync(out, s->row_ids.as<int64_t>() + row, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+    }
     return B200RAG_OK;
 }
 
@@ -799,9 +948,11 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
     uint8_t* d = s->ws.out.as<uint8_t>();
     int32_t* amb = (int32_t*)(d + o_cnt) + B;
     const int saved_slack = s->slack;
+    const bool saved_exhaustive = s->exhaustive;
     int retries = 0;
     int launches = 0;
     int rc = B200RAG_OK;
+    bool unresolved = false;
     // results land in the tail of the pinned block (the head still feeds the query H2D)
     uint8_t* hres = (uint8_t*)s->h_pinned + (s->h_pinned_cap - al256(out_bytes) - 256);
     hres = (uint8_t*)(((uintptr_t)hres) & ~(uintptr_t)255);
@@ -821,13 +972,29 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
         if (e != cudaSuccess) { rc = cuda_fail(e, "result read-back"); break; }
         launches += s->stats.kernel_launches;
         const int32_t ambiguous = ((const int32_t*)(hres + o_cnt))[B];
+        if (ambiguous == 0) break;
         const int cur = s->slack > 0 ? s->slack : default_slack(L);
-        if (ambiguous == 0 || L + cur >= 3 * B200RAG_MAX_TOPK || retries >= 6) break;
+        if (s->exhaustive) { unresolved = true; break; }          // cannot happen: the exhaustive legs never flag
+        if (L + cur >= 3 * B200RAG_MAX_TOPK || retries >= 6) {
+            // The slack guard never cleared (massive ties / near-duplicate scores around the cut).  Recompute the legs
+            // exhaustively -- exact by construction -- or, when that is disabled, refuse to return a guess.
+            if (!s->exact_fallback) { unresolved = true; break; }
+            s->exhaustive = true;
+            ++retries;
+            continue;
+        }
         s->slack = std::min(cur * 2 + L, 3 * B200RAG_MAX_TOPK - L);  // widen and redo the legs
         ++retries;
     }
     s->slack = saved_slack;
+    s->exhaustive = saved_exhaustive;
     if (rc != B200RAG_OK) return rc;
+    if (unresolved) {
+        set_error("search: the slack guard never cleared (ties or near-duplicate scores around the top-k cut) and the "
+                  "exhaustive exact pass is disabled (b200rag_set_exact_fallback / B200RAG_EXACT_FALLBACK)");
+        s->stats.retries = retries;
+        return B200RAG_ERR_INEXACT;
+    }
     memcpy(out_ids, hres + o_ids, (size_t)B * K * 8);
     memcpy(out_scores, hres + o_sc, (size_t)B * K * 8);
     memcpy(out_counts, hres + o_cnt, (size_t)B * 4);
@@ -841,7 +1008,7 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
 // ---- persistence -------------------------------------------------------------------------------------------------
 struct ShardFileHeader {
     char magic[8];            // "B200RAG1"
-    int32_t version, dim, vocab, reserved;
+    int32_t version, dim, vocab, reserved;   // version 2 appends the global row ids (i64 [n_rows]) after the weights
     int64_t n_rows, nnz;
 };
 
@@ -874,7 +1041,7 @@ extern "C" int b200rag_save(b200rag_shard* sp, const char* path) {
     if (f == nullptr) { set_error(std::string("save: cannot open ") + path); return B200RAG_ERR_INVALID; }
     ShardFileHeader h{};
     memcpy(h.magic, "B200RAG1", 8);
-    h.version = 1; h.dim = s->dim; h.vocab = s->vocab; h.n_rows = s->n_rows; h.nnz = s->nnz;
+    h.version = 2; h.dim = s->dim; h.vocab = s->vocab; h.n_rows = s->n_rows; h.nnz = s->nnz;
     const size_t stage_bytes = (size_t)64 << 20;
     void* stage = nullptr;
     int rc = B200RAG_OK;
@@ -884,6 +1051,7 @@ extern "C" int b200rag_save(b200rag_shard* sp, const char* path) {
     if (rc == B200RAG_OK) rc = dev_to_file(s, s->fwd_ptr.p, (size_t)(s->n_rows + 1) * 8, f, stage, stage_bytes);
     if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_terms.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
     if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_w.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->row_ids.p, (size_t)s->n_rows * 8, f, stage, stage_bytes);
     cudaFreeHost(stage);
     if (fclose(f) != 0 && rc == B200RAG_OK) { set_error("save: close failed"); rc = B200RAG_ERR_INVALID; }
     return rc;
@@ -897,7 +1065,7 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
     FILE* f = fopen(path, "rb");
     if (f == nullptr) { set_error(std::string("load: cannot open ") + path); return B200RAG_ERR_INVALID; }
     ShardFileHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "B200RAG1", 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "B200RAG1", 8) != 0 || (h.version != 1 && h.version != 2)) {
         fclose(f); set_error("load: not a b200rag shard file"); return B200RAG_ERR_INVALID;
     }
     if (h.dim != s->dim || h.vocab != s->vocab || h.n_rows < 0 || h.nnz < 0 || h.n_rows > 0xFFFFFFF0ll) {
@@ -915,11 +1083,30 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
     if (rc == B200RAG_OK) rc = file_to_dev(s, s->fwd_ptr.p, (size_t)(h.n_rows + 1) * 8, f, stage, stage_bytes);
     if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_terms.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
     if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_w.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
+    if (rc == B200RAG_OK) rc = s->row_ids.ensure((size_t)std::max<int64_t>(h.n_rows, 1) * 8, 0, st);
+    int64_t last_id = INT64_MIN;
+    if (rc == B200RAG_OK && h.n_rows > 0) {
+        if (h.version >= 2) rc = file_to_dev(s, s->row_ids.p, (size_t)h.n_rows * 8, f, stage, stage_bytes);
+        else rc = launch_fill_row_ids(s, s->row_ids.as<int64_t>(), s->cfg.row_base, h.n_rows);
+        if (rc == B200RAG_OK) {
+            cudaError_t e = cudaMemcpyAsync(&last_id, s->row_ids.as<int64_t>() + (h.n_rows - 1), 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "load: row ids");
+        }
+    }
     cudaFreeHost(stage);
     fclose(f);
-    if (rc != B200RAG_OK) { s->n_rows = 0; s->nnz = 0; return rc; }
+    if (rc != B200RAG_OK) {
+        // leave a clean empty shard behind: the forward index's first word is what append_rows builds on
+        const std::string msg = g_err;
+        s->n_rows = 0; s->nnz = 0; s->last_id = INT64_MIN;
+        if (s->fwd_ptr.p != nullptr) { cudaMemsetAsync(s->fwd_ptr.p, 0, 8, st); cudaStreamSynchronize(st); cudaGetLastError(); }
+        g_err = msg;
+        return rc;
+    }
     s->n_rows = h.n_rows;
     s->nnz = h.nnz;
+    s->last_id = last_id;
     s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0; s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->h_blk_base.clear();
     return build_inverted(s);
@@ -963,6 +1150,7 @@ int b200rag_p2p_export(b200rag_shard* sp, int32_t world, int64_t slot_bytes, uin
     s->x_world = world;
     s->x_slot_bytes = slot_bytes;
     s->x_epoch = 0;
+    if (const char* e = getenv("B200RAG_P2P_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms > 0) s->x_timeout_cycles = ms * 2000000ll; }
     return B200RAG_OK;
 }
 

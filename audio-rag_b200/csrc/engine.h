@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 
 #include <map>
 #include <string>
@@ -85,6 +86,9 @@ struct Workspace {
     DevBuf pool;          // filter path of the tcgen05 kernel: [B, cap] u64 keys | [B] i32 counters
     DevBuf cands;         // [nlegs, B, L] b200rag_cand  (single-shard search)
     DevBuf out;           // [B*top_k i64 ids | B*top_k f64 scores | B+1 i32 counts, ambiguous flag]
+    DevBuf ex_keys;       // exhaustive path: [n_rows] u64 keys (all eligible rows -> exact keys)
+    DevBuf ex_sorted;     // exhaustive path: [n_rows] u64 sorted keys
+    DevBuf ex_temp;       // exhaustive path: cub temporary storage
 };
 
 // A staged query batch: its device block and the host-side facts `legs`/`fuse` need.  b200rag_stage fills slot 0;
@@ -125,10 +129,14 @@ struct Shard {
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
+    bool exhaustive = false;      // legs score EVERY eligible row canonically and sort (always exact; exact.cu)
+    bool exact_fallback = true;   // b200rag_search falls back to the exhaustive pass when the slack guard never clears
 
     // dense rows
     int64_t n_rows = 0;
     DevBuf dense;  // [n_rows, dim] bf16 bits
+    DevBuf row_ids;               // i64 [n_rows] global id of every local row, strictly increasing (R1, R5)
+    int64_t last_id = INT64_MIN;  // largest id stored so far
 
     // forward (doc-major) sparse index, kept for the exact re-score and for rebuilds
     int64_t nnz = 0;
@@ -177,6 +185,7 @@ struct Shard {
     int x_rank = 0, x_world = 0;
     int64_t x_slot_bytes = 0;
     unsigned long long x_epoch = 0;
+    long long x_timeout_cycles = 4000000000ll;   // fuse gives up on a peer after this many SM cycles (~2 s)
     cudaStream_t x_stream = nullptr;      // exchange + fuse stream (nullptr = the shard's stream)
 
     // pinned host staging for results
@@ -202,8 +211,11 @@ int launch_dense_gemm_filtered(Shard* s, int batch, int Lc, uint64_t* scratch_a,
 // Reduce [batch, n_lists, Lc] key lists to [batch, Lc] (sorted desc) with a tree of smem bitonic merges.
 // `a` holds the input; `a`/`b` are used ping-pong; *result points at the final [batch, Lc] list.
 int launch_merge_tree(Shard* s, int batch, int n_lists, int Lc, uint64_t* a, uint64_t* b, uint64_t** result);
-int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact);
-int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact);
+// q0: first query of the staged batch these `batch` lists belong to; drop_untouched (sparse): a row sharing no term
+// with the query gets key 0 (the scans never select such rows; the exhaustive path feeds every row)
+int launch_rescore_dense(Shard* s, int batch, int64_t Lc, const uint64_t* approx, uint64_t* exact, int q0 = 0);
+int launch_rescore_sparse(Shard* s, int batch, int64_t Lc, const uint64_t* approx, uint64_t* exact, int q0 = 0,
+                          bool drop_untouched = false);
 // sort exact keys, apply threshold, slack guard, emit b200rag_cand [batch, L]
 int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* approx, const uint64_t* exact,
                         float eps_abs, float eps_rel, const float* eps_abs_q /*[batch] or null*/, int has_thr, float thr,
@@ -219,6 +231,13 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
 int launch_exchange(Shard* s, const void* mine, int64_t nbytes, void* const* peer_windows_dev, int world, int rank,
                     int64_t slot_bytes, int parity, unsigned long long epoch);
 constexpr int kFlagStrideU64 = 16;   // exchange flags sit 128 bytes apart
+
+// ---- exact.cu ------------------------------------------------------------------------------------------
+// Exhaustive exact leg: canonical score of every eligible row, full sort, first L -> out[batch][L].  Never ambiguous.
+int launch_exhaustive_leg(Shard* s, bool sparse, int batch, int L, int has_thr, float thr, b200rag_cand* out);
+// Drop the rows whose keep bit is clear (keep_words on the device, one bit per local row).
+int compact_rows(Shard* s, const uint32_t* keep_words_dev);
+int launch_fill_row_ids(Shard* s, int64_t* dst, int64_t first_id, int64_t n);
 
 // ---- sparse.cu -----------------------------------------------------------------------------------------
 int build_inverted(Shard* s);

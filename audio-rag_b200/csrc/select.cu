@@ -68,10 +68,10 @@ __device__ __forceinline__ double bf16hi_d(uint32_t u) { return (double)__uint_a
 __global__ void __launch_bounds__(256) rescore_dense_kernel(const uint16_t* __restrict__ corpus, int dim,
                                                             const uint16_t* __restrict__ q_bits,
                                                             const uint64_t* __restrict__ approx,
-                                                            uint64_t* __restrict__ exact, int Lc) {
-    const int q = blockIdx.y;
+                                                            uint64_t* __restrict__ exact, int64_t Lc, int q0) {
+    const int q = blockIdx.y;                 // list index; the query it belongs to is q0 + q
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + w;
+    const int64_t i = (int64_t)blockIdx.x * 8 + w;
     if (i >= Lc) return;
     const uint64_t key = approx[(size_t)q * Lc + i];
     if (key == 0) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) rescore_dense_kernel(const uint16_t* __re
     }
     const uint32_t row = key_row(key);
     const uint4* rp = reinterpret_cast<const uint4*>(corpus + (size_t)row * dim);
-    const uint4* qp = reinterpret_cast<const uint4*>(q_bits + (size_t)q * dim);
+    const uint4* qp = reinterpret_cast<const uint4*>(q_bits + (size_t)(q0 + q) * dim);
     const int nch = dim / 256;
     uint4 cv[4], qv[4];
 #pragma unroll
@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(256) rescore_dense_kernel(const uint16_t* __re
     if (lane == 0) exact[(size_t)q * Lc + i] = make_key(__double2float_rn(acc) + 0.0f, row);
 }
 
-int launch_rescore_dense(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact) {
-    dim3 grid((Lc + 7) / 8, batch);
+int launch_rescore_dense(Shard* s, int batch, int64_t Lc, const uint64_t* approx, uint64_t* exact, int q0) {
+    dim3 grid((unsigned)((Lc + 7) / 8), batch);
     rescore_dense_kernel<<<grid, 256, 0, s->stream>>>(s->dense.as<uint16_t>(), s->dim,
-                                                      s->ws.q_bits.as<uint16_t>(), approx, exact, Lc);
+                                                      s->ws.q_bits.as<uint16_t>(), approx, exact, Lc, q0);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;
@@ -121,21 +121,23 @@ __global__ void __launch_bounds__(256) rescore_sparse_kernel(const int64_t* __re
                                                              const uint32_t* __restrict__ q_terms,
                                                              const float* __restrict__ q_w,
                                                              const uint64_t* __restrict__ approx,
-                                                             uint64_t* __restrict__ exact, int Lc) {
+                                                             uint64_t* __restrict__ exact, int64_t Lc, int q0,
+                                                             int drop_untouched) {
     __shared__ uint32_t qt[kMaxQueryTermsChunk];
     __shared__ float qw[kMaxQueryTermsChunk];
     __shared__ double prod[8][kMaxQueryTermsChunk];
     __shared__ uint8_t present[8][kMaxQueryTermsChunk];
-    const int q = blockIdx.y;
+    const int q = blockIdx.y;                 // list index; the query it belongs to is q0 + q
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + w;
+    const int64_t i = (int64_t)blockIdx.x * 8 + w;
     const uint64_t key = i < Lc ? approx[(size_t)q * Lc + i] : 0ull;
     const bool active = key != 0;
     const uint32_t row = key_row(key);
     int64_t ds = 0, de = 0;
     if (active) { ds = fwd_ptr[row]; de = fwd_ptr[row + 1]; }
-    const int64_t qs = q_indptr[q], qe = q_indptr[q + 1];
+    const int64_t qs = q_indptr[q0 + q], qe = q_indptr[q0 + q + 1];
     double acc = 0.0;
+    int touched = 0;
     for (int64_t c0 = qs; c0 < qe; c0 += kMaxQueryTermsChunk) {
         const int cn = (int)min((int64_t)kMaxQueryTermsChunk, qe - c0);
         __syncthreads();
@@ -156,20 +158,21 @@ __global__ void __launch_bounds__(256) rescore_sparse_kernel(const int64_t* __re
             __syncwarp();
             if (lane == 0)
                 for (int j = 0; j < cn; ++j)
-                    if (present[w][j]) acc = __dadd_rn(acc, prod[w][j]);
+                    if (present[w][j]) { acc = __dadd_rn(acc, prod[w][j]); touched = 1; }
             __syncwarp();
         }
     }
     if (i < Lc && lane == 0)
-        exact[(size_t)q * Lc + i] = active ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
+        exact[(size_t)q * Lc + i] = (active && (touched || !drop_untouched)) ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
 }
 
-int launch_rescore_sparse(Shard* s, int batch, int Lc, const uint64_t* approx, uint64_t* exact) {
-    dim3 grid((Lc + 7) / 8, batch);
+int launch_rescore_sparse(Shard* s, int batch, int64_t Lc, const uint64_t* approx, uint64_t* exact, int q0,
+                          bool drop_untouched) {
+    dim3 grid((unsigned)((Lc + 7) / 8), batch);
     rescore_sparse_kernel<<<grid, 256, 0, s->stream>>>(s->fwd_ptr.as<int64_t>(), s->fwd_terms.as<uint32_t>(),
                                                        s->fwd_w.as<float>(), s->ws.q_sp_indptr.as<int64_t>(),
                                                        s->ws.q_sp_terms.as<uint32_t>(), s->ws.q_sp_w.as<float>(),
-                                                       approx, exact, Lc);
+                                                       approx, exact, Lc, q0, drop_untouched ? 1 : 0);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;
@@ -180,7 +183,8 @@ __global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __res
                                                            const uint64_t* __restrict__ exact, int Lc, int L,
                                                            int npow2, float eps_abs, float eps_rel,
                                                            const float* __restrict__ eps_abs_q, int has_thr,
-                                                           float thr, int64_t row_base, b200rag_cand* __restrict__ out,
+                                                           float thr, const int64_t* __restrict__ row_ids,
+                                                           b200rag_cand* __restrict__ out,
                                                            int32_t* __restrict__ ambiguous) {
     extern __shared__ __align__(16) uint64_t fkeys[];
     __shared__ int nvalid_s;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(256) finalize_leg_kernel(const uint64_t* __res
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const uint64_t k = fkeys[i];
         b200rag_cand c;
-        c.id = k != 0 ? row_base + (int64_t)key_row(k) : -1;
+        c.id = k != 0 ? row_ids[key_row(k)] : -1;
         c.score = k != 0 ? key_score(k) : 0.f;
         c.valid = k != 0 ? 1u : 0u;
         out[(size_t)q * L + i] = c;
@@ -228,7 +232,7 @@ int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* appr
                         b200rag_cand* out, int32_t* ambiguous) {
     const int npow2 = next_pow2(Lc);
     finalize_leg_kernel<<<batch, 256, (size_t)npow2 * 8, s->stream>>>(approx, exact, Lc, L, npow2, eps_abs, eps_rel,
-                                                                      eps_abs_q, has_thr, thr, s->cfg.row_base, out, ambiguous);
+                                                                      eps_abs_q, has_thr, thr, s->row_ids.as<int64_t>(), out, ambiguous);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;
@@ -291,7 +295,7 @@ struct TailParams {
     const float* eps_abs_q;
     int has_thr;
     float thr;
-    int64_t row_base;
+    const int64_t* row_ids;  // [n_rows] global id of a local row
     b200rag_cand* out;       // [batch][L]
     int32_t* ambiguous;
 };
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
     for (int i = tid; i < p.L; i += NT) {
         const uint64_t k = tkeys[i];
         b200rag_cand c;
-        c.id = k != 0 ? p.row_base + (int64_t)key_row(k) : -1;
+        c.id = k != 0 ? p.row_ids[key_row(k)] : -1;
         c.score = k != 0 ? key_score(k) : 0.f;
         c.valid = k != 0 ? 1u : 0u;
         p.out[(size_t)q * p.L + i] = c;
@@ -485,7 +489,7 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
     p.fwd_ptr = s->fwd_ptr.as<int64_t>(); p.fwd_terms = s->fwd_terms.as<uint32_t>(); p.fwd_w = s->fwd_w.as<float>();
     p.q_indptr = s->ws.q_sp_indptr.as<int64_t>(); p.q_terms = s->ws.q_sp_terms.as<uint32_t>(); p.q_w = s->ws.q_sp_w.as<float>();
     p.eps_abs = eps_abs; p.eps_rel = eps_rel; p.eps_abs_q = eps_abs_q; p.has_thr = has_thr; p.thr = thr;
-    p.row_base = s->cfg.row_base; p.out = out; p.ambiguous = ambiguous;
+    p.row_ids = s->row_ids.as<int64_t>(); p.out = out; p.ambiguous = ambiguous;
     const size_t smem = (size_t)kTailSurvivorCap * 8;
     static AttrCache attr;
     if (attr.raise(s->cfg.device, smem)) {     // static + dynamic shared memory exceeds the 48 KB default of the sparse flavour
@@ -528,7 +532,8 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
                                                    int L, int top_k, int rrf_k,
                                                    int64_t* __restrict__ out_ids, double* __restrict__ out_scores,
                                                    int32_t* __restrict__ out_counts,
-                                                   const unsigned long long* wait_flags, unsigned long long wait_epoch) {
+                                                   const unsigned long long* wait_flags, unsigned long long wait_epoch,
+                                                   long long timeout_cycles) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const int M = n_shards * L;
     b200rag_cand* stage = reinterpret_cast<b200rag_cand*>(fsm);
@@ -544,9 +549,16 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
     if (threadIdx.x == 0) total_s = 0;
     if (wait_flags != nullptr) {
         // peer-memory exchange: every shard's block is complete once its flag carries this search's epoch
+        // out_counts[batch + 1] is a STICKY latch (zeroed once by the caller, set by any block that ever gave up on a
+        // peer): a block that finds it set does not wait at all, so one timeout empties every query of this and of all
+        // later searches instead of leaving a mix of fused and emptied queries (the ranks' epochs have diverged)
         __shared__ int timed_out;
-        if (threadIdx.x == 0) timed_out = 0;
+        if (threadIdx.x == 0) timed_out = *reinterpret_cast<volatile int32_t*>(&out_counts[batch + 1]) != 0 ? 1 : 0;
         __syncthreads();
+        if (timed_out) {
+            if (threadIdx.x == 0) { out_counts[q] = 0; if (q == 0) out_counts[batch] = -1; }
+            return;
+        }
         if (threadIdx.x < n_shards) {
             const unsigned long long* f = wait_flags + (size_t)threadIdx.x * kFlagStrideU64;
             const long long t0 = clock64();
@@ -554,12 +566,16 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
                 unsigned long long v;
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
                 if (v >= wait_epoch) break;
-                if (clock64() - t0 > 4000000000ll) { timed_out = 1; break; }   // ~2 s: a peer is gone
+                if (clock64() - t0 > timeout_cycles) { timed_out = 1; break; }   // a peer is gone
             }
         }
         __syncthreads();
         if (timed_out) {
-            if (threadIdx.x == 0) { out_counts[q] = 0; if (q == 0) out_counts[batch] = -1; }
+            if (threadIdx.x == 0) {
+                atomicExch(&out_counts[batch + 1], 1);
+                out_counts[q] = 0;
+                if (q == 0) out_counts[batch] = -1;
+            }
             return;
         }
     }
@@ -733,7 +749,8 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
     const int fuse_threads = (size_t)n_shards * L > 512 ? 1024 : 256;     // the bitonic merge of large sets wants more lanes
     fuse_kernel<<<batch, fuse_threads, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
-                                                 rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch);
+                                                 rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch,
+                                                 s->x_timeout_cycles);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return B200RAG_OK;

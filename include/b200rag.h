@@ -34,6 +34,8 @@ extern "C" {
 #define B200RAG_ERR_NOGPU 3   /* no usable sm_100 device                          */
 #define B200RAG_ERR_OOM 4     /* device allocation failed                         */
 #define B200RAG_ERR_STATE 5   /* call order violated (e.g. search before build)   */
+#define B200RAG_ERR_INEXACT 6 /* the slack guard never cleared and the exhaustive exact pass is disabled:
+                                 the result could differ from the exact top-k, so none is returned            */
 
 /* search_type of QdrantRetriever.search (qdrant.py:233,250,272,299,313) */
 #define B200RAG_DENSE 0
@@ -94,6 +96,18 @@ void b200rag_shard_destroy(b200rag_shard* s);
 int b200rag_set_stream(b200rag_shard* s, void* cuda_stream);
 int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximate candidates per leg before the
                                                                 exact re-score (0 = default max(16, L/2))      */
+/* Exactness contract.  The scans select Lc = L + slack candidates by APPROXIMATE score and re-score them exactly; a
+ * guard flags a leg as ambiguous when a row outside the candidates could still belong to the exact top-L (massive
+ * ties, near-duplicate scores around the cut).  b200rag_search then widens the slack and repeats; if the guard still
+ * has not cleared when the slack reaches its cap, the legs are recomputed EXHAUSTIVELY: every eligible row is scored in
+ * the canonical order and the top-L are taken from a full sort (always exact, ~10x the cost of a scan).
+ *   set_exhaustive(1)      make b200rag_legs take the exhaustive path directly (multi-shard callers use it for their own
+ *                          last retry; tests use it as an independent in-library cross-check of the scan kernels);
+ *   set_exact_fallback(0)  disable the automatic exhaustive pass: b200rag_search then fails with
+ *                          B200RAG_ERR_INEXACT instead of returning a result whose guard never cleared
+ *                          (default 1; the environment variable B200RAG_EXACT_FALLBACK=0 sets the default to 0). */
+int b200rag_set_exhaustive(b200rag_shard* s, int32_t on);
+int b200rag_set_exact_fallback(b200rag_shard* s, int32_t on);
 /* Dense kernel choice: 0 = auto (bulk-copy SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT scan,
  * 2 = tcgen05 GEMM.  Both produce bit-identical results (candidates are re-scored in the canonical order). */
 int b200rag_set_dense_path(b200rag_shard* s, int32_t path);
@@ -109,14 +123,40 @@ int b200rag_add(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_host, co
 /* Same with device-resident inputs (bulk / synthetic ingest). nnz = indptr[n]. */
 int b200rag_add_device(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_dev, const int64_t* sp_indptr_dev,
                        const uint32_t* sp_terms_dev, const float* sp_weights_dev, int64_t nnz);
+/* The same two calls with explicit GLOBAL row ids (host array [n]; NULL = cfg.row_base + local row, which is what
+ * b200rag_add / b200rag_add_device assign).  Ids must be strictly increasing over the shard's lifetime, so that the
+ * order of local rows is the order of global ids and the tie-break of SURVEY R5 (smaller row id first) is the same
+ * on one shard and on any row-partition of the corpus.  A plugin that spreads one insertion-ordered row space over
+ * several shards (B200Retriever with shards > 1) routes each add() batch to a shard and passes the rows' global ids. */
+int b200rag_add_ids(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_host, const int64_t* sp_indptr_host,
+                    const uint32_t* sp_terms_host, const float* sp_weights_host, const int64_t* ids_host);
+int b200rag_add_device_ids(b200rag_shard* s, int64_t n, const uint16_t* dense_bits_dev, const int64_t* sp_indptr_dev,
+                           const uint32_t* sp_terms_dev, const float* sp_weights_dev, int64_t nnz,
+                           const int64_t* ids_host);
+/* GPU-side ingest pack: RAW fp32 vectors from the host (what an embedder returns, embeddings/bge.py:125)
+ * are copied to the device and normalised + rounded to bf16 there (b200rag_normalize_bf16_device: bit-equal to the
+ * host routine), so add() does not spend host time on the corpus rows.  CSR and ids as in b200rag_add_ids. */
+int b200rag_add_f32(b200rag_shard* s, int64_t n, const float* dense_f32_host, const int64_t* sp_indptr_host,
+                    const uint32_t* sp_terms_host, const float* sp_weights_host, const int64_t* ids_host);
+/* Physically drop rows (delete_collection, qdrant.py:354-363: the reference drops the collection's storage).
+ * keep_words_host: bit (r & 31) of word (r >> 5) set <=> local row r survives; n_rows_mask must equal the shard's row
+ * count.  Surviving rows keep their order and their global ids; dense rows, the forward index and the id map are
+ * rewritten on the device, the inverted index is rebuilt on the next sparse search (or b200rag_build).  Every mask
+ * and staged batch of the shard is dropped (their bit positions are local rows). */
+int b200rag_compact(b200rag_shard* s, const uint32_t* keep_words_host, int64_t n_rows_mask);
 /* Bring the block-major inverted index up to date with the rows added so far (incremental). */
 int b200rag_build(b200rag_shard* s);
 int64_t b200rag_count(const b200rag_shard* s);    /* rows in the shard (client.get_collection().points_count, qdrant.py:369-370) */
 int64_t b200rag_postings(const b200rag_shard* s); /* sparse non-zeros in the shard */
 /* Drop every row (delete_collection of the last collection, qdrant.py:354-363); keeps allocations. */
 int b200rag_clear(b200rag_shard* s);
-/* Test/debug read-back of stored rows. */
+/* Test/debug read-back of stored rows (the oracle checks of tests/ and bench.py score exactly these bits).
+ * read_sparse: indptr_out_host[n+1] (from 0) is always written; terms / weights only when both are non-NULL and
+ * cap_nnz >= indptr_out_host[n] (else B200RAG_ERR_INVALID, so a caller can size its arrays from a first call). */
 int b200rag_read_dense(b200rag_shard* s, int64_t row, int64_t n, uint16_t* out_bits_host);
+int b200rag_read_sparse(b200rag_shard* s, int64_t row, int64_t n, int64_t* indptr_out_host, uint32_t* terms_out_host,
+                        float* weights_out_host, int64_t cap_nnz);
+int b200rag_read_row_ids(b200rag_shard* s, int64_t row, int64_t n, int64_t* ids_out_host);
 
 /* ---- eligibility masks  (replace Filter(must=[FieldCondition...]) + the collection itself, qdrant.py:262-269) */
 /* Bit (r & 31) of word (r >> 5) set <=> local row r is eligible.  n_rows bits are read; rows beyond are ineligible. */
@@ -183,8 +223,12 @@ int b200rag_load(b200rag_shard* s, const char* path);
  *   fuse    : b200rag_fuse on the local window; the kernel itself waits (acquire at system scope) until all `world`
  *             flags carry the epoch, so there is no host synchronisation and no collective launch in the search.
  * Every rank must make the same sequence of exchange/fuse calls (SPMD).  A rank may run at most one search ahead
- * of its peers (its next fuse waits for their next epoch), which the two slot parities cover.  If a peer's flag does
- * not arrive within ~2 s the fuse gives up and reports out_counts_dev[batch] = -1. */
+ * of its peers (its next fuse waits for their next epoch), which the two slot parities cover.
+ * p2p_fuse writes batch + 2 ints to out_counts_dev: [batch] = sum of the shards' ambiguity counters (or -1), and
+ * [batch + 1] = a STICKY timeout latch which the caller zeroes once when it allocates the buffer: if a peer's flag
+ * does not arrive within the timeout (B200RAG_P2P_TIMEOUT_MS, default 2000) every block that gave up sets the latch
+ * and empties its query, so a partial timeout can never pass for a result.  After a timeout the ranks' epochs have
+ * diverged: close and re-export / re-attach the windows (ShardedSearcher.reset) before searching again. */
 #define B200RAG_IPC_HANDLE_BYTES 64
 int b200rag_p2p_export(b200rag_shard* s, int32_t world, int64_t slot_bytes, uint8_t* handle_out);
 int b200rag_p2p_attach(b200rag_shard* s, int32_t rank, int32_t world, const uint8_t* handles);
@@ -195,6 +239,22 @@ int b200rag_p2p_close(b200rag_shard* s);
  * search's scans start while this search still waits for its peers (the caller orders the two streams with events:
  * exchange after this search's legs; buffers reused only after the fuse that read them).  NULL = the shard's stream. */
 int b200rag_p2p_set_stream(b200rag_shard* s, void* cuda_stream);
+
+/* ---- shard group: several shards of one corpus driven by ONE process ----------------------------------------------
+ * The reference's retriever is one in-process object (pipeline/orchestrator.py:48-74), so behind the plugin the row
+ * sharding of the corpus over the GPUs of a box lives in the caller's process: a group holds `n` shards (one per GPU,
+ * or several per GPU), and group_search is b200rag_search over all of them -- on every shard stage + legs on a
+ * per-device worker thread, the candidate blocks gathered into the first shard's window by asynchronous peer copies
+ * ordered with CUDA events, then fuse + read-back on the first shard.  The result is bit-identical to one shard holding
+ * all rows (global ids and R5 order come from the shards' row ids, see b200rag_add_ids).  The shards stay owned by the
+ * caller (add / mask_set / compact are per shard; q->mask_ids name the SAME mask id on every shard) and must outlive
+ * the group.  Same retry / exhaustive-fallback / B200RAG_ERR_INEXACT contract as b200rag_search. */
+typedef struct b200rag_group b200rag_group;
+int b200rag_group_create(b200rag_shard* const* shards, int32_t n, b200rag_group** out);
+void b200rag_group_destroy(b200rag_group* g);
+int32_t b200rag_group_size(const b200rag_group* g);
+int b200rag_group_search(b200rag_group* g, const b200rag_query* q, int64_t* out_ids_host, double* out_scores_host,
+                         int32_t* out_counts_host);
 
 /* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
 typedef struct {
@@ -208,8 +268,11 @@ typedef struct {
     float sparse_scan_ms;        /* ... and of the sparse scan kernel (CUDA events on the shard's stream)      */
     float pre_scan_ms;           /* ... from the entry of `legs` to the start of the dense scan (launch latency)  */
     float tail_ms;               /* ... from the end of the dense scan to the end of the last `fuse`               */
+    int32_t exhaustive;          /* 1 = the last legs took the exhaustive exact path (set_exhaustive / fallback)   */
+    int32_t reserved;
 } b200rag_stats;
 int b200rag_get_stats(const b200rag_shard* s, b200rag_stats* out);
+int b200rag_group_get_stats(const b200rag_group* g, b200rag_stats* out); /* last group_search: launches summed over shards */
 /* With profiling on: event timings of the legs call made `steps_back` calls ago (0 = the last one, < 64), for callers
  * that enqueue many searches before synchronising; only the four *_ms fields of `out` are filled. */
 int b200rag_get_stats_step(const b200rag_shard* s, int32_t steps_back, b200rag_stats* out);

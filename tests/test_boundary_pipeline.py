@@ -7,7 +7,7 @@ import pytest
 
 import conftest
 from data_small import DIM, make_chunks, make_queries
-from oracle_shard import OracleShard
+from oracle_shard import OracleGroup, OracleShard
 
 pytestmark = pytest.mark.skipif(not conftest.HAVE_REFERENCE, reason="reference checkout not present")
 
@@ -42,14 +42,19 @@ def _rag(tmp_path):
     return AudioRAG(cfg), cfg
 
 
-def test_audio_rag_query_runs_on_b200_retriever(tmp_path):
+@pytest.mark.parametrize("n_shards", [1, 2])
+def test_audio_rag_query_runs_on_b200_retriever(tmp_path, n_shards):
+    """n_shards = 2: the reference's AudioRAG.query() on a retriever that owns TWO shards."""
     from audio_rag.core import AudioChunk, EmbeddingResult, SparseVector
     from b200rag.retriever import B200Retriever
     rag, cfg = _rag(tmp_path)
     retr = B200Retriever(cfg.retrieval, embedding_dim=DIM)
-    retr._shard = OracleShard(dim=DIM)
+    shards = [OracleShard(dim=DIM) for _ in range(n_shards)]
+    retr._set_shards(shards, OracleGroup(shards) if n_shards > 1 else None)
     ch, em = make_chunks(150, 61, "P", AudioChunk, EmbeddingResult, SparseVector)
-    retr.add(ch, em, "tenant_a")
+    for s in range(0, 150, 50):
+        retr.add(ch[s:s + 50], em[s:s + 50], "tenant_a")
+    assert all(sh.count > 0 for sh in shards)
     qs = make_queries(3, 62, 150, 61, EmbeddingResult, SparseVector)
     rag._embedder = StubEmbedder(qs)
     rag._retriever = retr                       # before first use: propagated to both pipelines

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_ffi.Cand) == 16 and _ffi.CAND_DTYPE.itemsize == 16
     assert ctypes.sizeof(_ffi.Config) == 40
     assert ctypes.sizeof(_ffi.Query) == 24 + 5 * 8
-    assert ctypes.sizeof(_ffi.Stats) == 48
+    assert ctypes.sizeof(_ffi.Stats) == 56
 
 
 def test_compute_fails_loudly_without_gpu(built_lib):

@@ -1,11 +1,16 @@
-"""Full-size checks (BASELINE.json sizes: 10M x 1024 + Zipf postings on one B200) through size-independent properties;
-the oracle only scores the handful of rows that are returned (regenerated on the host from the same generators).
+"""Full-size checks (BASELINE.json sizes: 10M x 1024 + Zipf postings on one B200).
 
+  * FULL-CORPUS ORACLE: the shard's stored rows are streamed back to the host and ALL 10M rows / documents are scored
+    by the C oracle for every checked query (tests/fullscale.py); the engine's complete per-leg top-L id lists, the
+    fused hybrid ids and every score must equal the oracle's bit for bit.  Covered: dense / sparse / hybrid top-10,
+    hybrid top-100 (L = 200 per leg), a 256-token (HyDE-length) sparse query, and BASELINE config 4's shape -- 1 000
+    Zipf-skewed collections, one 64-query hybrid batch with a per-query collection bitmask (largest, a mid-sized and a
+    small tenant checked against the oracle);
+  * the stored rows are the generators' rows (a 64k-row window regenerated on the host);
   * planted dense queries retrieve their planted row first (the generator's known answer);
-  * every returned (id, score) is bit-equal to the oracle's canonical score of that row, order is (score desc, id asc);
-  * no sampled row outside the result beats the last result (spot check of 200k rows);
   * a 2-shard split of the same corpus, fused, equals the single shard bit for bit (sharding invariance);
-  * the tcgen05 path and the SIMT path return identical results.
+  * the tcgen05 path, the SIMT path and the exhaustive exact path return identical results;
+  * every batched kernel returns what the single-query kernels return.
 """
 import os
 import sys
@@ -16,21 +21,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROWS = int(os.environ.get("B200RAG_FULLSIZE_ROWS", 10_000_000))
-
-
-def _host_rows(ids, dim=1024):
-    from b200rag import synth
-    return np.concatenate([synth.dense_rows_bf16(1234, int(i), 1, dim) for i in ids]) if len(ids) else \
-        np.zeros((0, dim), np.uint16)
-
-
-def _host_docs(ids, thr, tables):
-    from b200rag import synth
-    out = []
-    for i in ids:
-        ip, tt, ww = synth.sparse_docs_csr(1234, int(i), 1, ROWS, synth.VOCAB, 256, thr, tables)
-        out.append((tt, ww))
-    return out
+N_COLL = 1000
 
 
 @pytest.fixture(scope="module")
@@ -52,10 +43,132 @@ def big(gpu):
         s.close()
 
 
+def _eq(got_ids, got_sc, got_cnt, exp_ids, exp_sc, ctx):
+    assert int(got_cnt) == len(exp_ids), f"{ctx}: count {int(got_cnt)} != {len(exp_ids)}"
+    assert np.array_equal(got_ids[:len(exp_ids)], exp_ids), f"{ctx}: ids differ\n got {got_ids[:len(exp_ids)]}\n exp {exp_ids}"
+    assert np.array_equal(np.asarray(got_sc[:len(exp_ids)], np.float64), np.asarray(exp_sc, np.float64)), f"{ctx}: scores differ"
+
+
+def test_fullsize_full_corpus_oracle(big):
+    """Every checked query: the oracle scores ALL rows; complete leg lists, fused ids and scores compared at tolerance 0."""
+    import torch
+    from b200rag import normalize_bf16, synth
+    from fullscale import LegJob, stream_oracle_legs
+    from oracle import fast
+    one, _, _, dev = big
+    thr = synth.zipf_thresholds(synth.VOCAB)
+
+    # ---- queries
+    nq = 3
+    qf = synth.dense_queries_f32(2000, 0, nq, ROWS, 1024, corpus_seed=1234)
+    ip, tt, ww = synth.sparse_queries(2000, 0, nq)
+    qb = normalize_bf16(qf)
+    lf = synth.dense_queries_f32(2000, 500, 1, ROWS, 1024, corpus_seed=1234)          # HyDE-length query: 256 tokens
+    lip, ltt, lww = synth.sparse_queries(2000, 500, 1, n_tokens=256)
+    lb = normalize_bf16(lf)
+    assert lip[1] > 100, "the long query should have well over 100 distinct terms"
+    # config 4: a batch of 64 queries, each against its own collection (Zipf over 1 000 tenants, like the rows)
+    B4 = 64
+    cf = synth.dense_queries_f32(2000, 1000, B4, ROWS, 1024, corpus_seed=1234)
+    cip, ctt, cww = synth.sparse_queries(2000, 1000, B4)
+    cb = normalize_bf16(cf)
+    colls = synth.row_collections(99, 0, B4, N_COLL)
+    cthr = synth.zipf_thresholds(N_COLL)
+    cthr_dev = torch.from_numpy(cthr.view(np.int64)).to(dev)
+    words = torch.empty((ROWS + 31) // 32, dtype=torch.int32, device=dev)
+    mask_of = {}
+    for c in sorted(set(int(x) for x in colls)):
+        one.synth_collection_mask(1234, 0, ROWS, cthr_dev, N_COLL, c, words)
+        one.mask_set(100 + c, words, ROWS)
+        mask_of[c] = 100 + c
+    del words
+    order = np.argsort(colls, kind="stable")
+    probe4 = sorted({int(order[0]), int(order[len(order) // 2]), int(order[-1])})   # largest, a mid-sized, a small tenant
+
+    def elig_of(c):
+        return lambda lo, hi: synth.row_collections(1234, lo, hi - lo, N_COLL, cthr) == c
+
+    jobs = [LegJob(qb[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]], L=20) for i in range(2)]
+    jobs.append(LegJob(qb[2], tt[ip[2]:ip[3]], ww[ip[2]:ip[3]], L=200))                 # top-100 hybrid
+    jobs.append(LegJob(lb[0], ltt, lww, L=20))                                           # 256-token query
+    for i in probe4:
+        jobs.append(LegJob(cb[i], ctt[cip[i]:cip[i + 1]], cww[cip[i]:cip[i + 1]], L=20, eligible=elig_of(int(colls[i]))))
+
+    # ---- the stored rows are the generators' rows (one 64k window), then stream everything through the oracle
+    win = (ROWS // 3) // 65536 * 65536
+    tables = synth.bm25_tables(ROWS)
+
+    def check_rows(lo, bits, rip, rtt, rww):
+        if lo <= win < lo + len(bits):
+            o = win - lo
+            m = min(65536, len(bits) - o)
+            assert np.array_equal(bits[o:o + m], fast.synth_dense_bf16(1234, win, m, 1024))
+            gi, gt, gw = fast.synth_sparse_csr(1234, win, m, thr, tables[0], tables[1], synth.VOCAB, 256,
+                                                synth.TERM_PERM_MUL % synth.VOCAB)
+            assert np.array_equal(rip[o:o + m + 1] - rip[o], gi)
+            assert np.array_equal(rtt[rip[o]:rip[o + m]], gt) and np.array_equal(rww[rip[o]:rip[o + m]], gw)
+
+    stream_oracle_legs(one, jobs, check_rows=check_rows)
+
+    # ---- plain top-10: each leg's COMPLETE list (depth 20 and 10), and the fusion
+    tgt = synth.query_target_rows(2000, np.arange(nq), ROWS)
+    for i in range(2):
+        j = jobs[i]
+        sl = (ip[i:i + 2] - ip[i], tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]])
+        for k in (10, 20):
+            ids, sc, cnt = one.search("dense", k, qb[i:i + 1])
+            _eq(ids[0], sc[0], cnt[0], j.dense[0][:k], j.dense[1][:k], f"dense top-{k} q{i}")
+            ids, sc, cnt = one.search("sparse", k, qb[i:i + 1], *sl)
+            _eq(ids[0], sc[0], cnt[0], j.sparse[0][:k], j.sparse[1][:k], f"sparse top-{k} q{i}")
+        assert j.dense[0][0] == tgt[i], "the planted row is the oracle's best dense hit"
+        ids, sc, cnt = one.search("hybrid", 10, qb[i:i + 1], *sl)
+        ei, es = j.hybrid(10)
+        _eq(ids[0], sc[0], cnt[0], ei, es, f"hybrid top-10 q{i}")
+        # the same through the tcgen05 path and through the exhaustive exact path
+        one.set_dense_path(2)
+        g = one.search("hybrid", 10, qb[i:i + 1], *sl)
+        one.set_dense_path(0)
+        _eq(g[0][0], g[1][0], g[2][0], ei, es, f"hybrid top-10 q{i} (tcgen05)")
+    one.set_exhaustive(True)
+    g = one.search("hybrid", 10, qb[0:1], ip[0:2], tt[ip[0]:ip[1]], ww[ip[0]:ip[1]])
+    assert one.stats()["exhaustive"] == 1
+    one.set_exhaustive(False)
+    _eq(g[0][0], g[1][0], g[2][0], *jobs[0].hybrid(10), "hybrid top-10 q0 (exhaustive)")
+
+    # ---- top-100 hybrid (legs of 200)
+    j = jobs[2]
+    sl = (ip[2:4] - ip[2], tt[ip[2]:ip[3]], ww[ip[2]:ip[3]])
+    ids, sc, cnt = one.search("dense", 100, qb[2:3])
+    _eq(ids[0], sc[0], cnt[0], j.dense[0][:100], j.dense[1][:100], "dense top-100")
+    ids, sc, cnt = one.search("sparse", 100, qb[2:3], *sl)
+    _eq(ids[0], sc[0], cnt[0], j.sparse[0][:100], j.sparse[1][:100], "sparse top-100")
+    ids, sc, cnt = one.search("hybrid", 100, qb[2:3], *sl)
+    _eq(ids[0], sc[0], cnt[0], *j.hybrid(100), "hybrid top-100")
+
+    # ---- 256-token query
+    j = jobs[3]
+    ids, sc, cnt = one.search("sparse", 20, lb, lip, ltt, lww)
+    _eq(ids[0], sc[0], cnt[0], j.sparse[0], j.sparse[1], "sparse top-20, 256-token query")
+    ids, sc, cnt = one.search("hybrid", 10, lb, lip, ltt, lww)
+    _eq(ids[0], sc[0], cnt[0], *j.hybrid(10), "hybrid top-10, 256-token query")
+
+    # ---- config 4: ONE batch of 64 masked hybrid queries
+    mids = np.asarray([mask_of[int(c)] for c in colls], dtype=np.int32)
+    ids, sc, cnt = one.search("hybrid", 10, cb, cip, ctt, cww, mask_ids=mids)
+    assert one.stats()["dense_path"] == 2
+    for n_, i in enumerate(probe4):
+        _eq(ids[i], sc[i], cnt[i], *jobs[4 + n_].hybrid(10), f"config-4 batch, query {i} (collection {int(colls[i])})")
+    # every hit of every query of the batch belongs to the query's collection
+    rc_all = synth.row_collections(1234, 0, ROWS, N_COLL, cthr)
+    for i in range(B4):
+        assert (rc_all[ids[i, :cnt[i]]] == colls[i]).all(), f"config-4 query {i}: a hit outside its collection"
+    for m in mask_of.values():
+        one.mask_drop(m)
+
+
 def test_fullsize_properties(big):
     import torch
     from b200rag import Shard, normalize_bf16, synth
-    from oracle import oracle
     one, a, b, dev = big
     assert one.count == ROWS and a.count + b.count == ROWS
     nq, k = 4, 10
@@ -63,42 +176,13 @@ def test_fullsize_properties(big):
     ip, tt, ww = synth.sparse_queries(2000, 0, nq)
     qb = normalize_bf16(qf)
     tgt = synth.query_target_rows(2000, np.arange(nq), ROWS)
-    thr = synth.zipf_thresholds(synth.VOCAB)
-    tables = synth.bm25_tables(ROWS)
 
-    # ---- dense: planted row first, exact scores, ordering, spot check
     ids, sc, cnt = one.search("dense", k, qb)
     for i in range(nq):
         assert cnt[i] == k and ids[i, 0] == tgt[i]
-        exp = oracle.dense_scores(_host_rows(ids[i]), qb[i])
-        assert np.array_equal(sc[i].astype(np.float32), exp), "dense scores differ from the oracle"
         assert all(sc[i, j] > sc[i, j + 1] or (sc[i, j] == sc[i, j + 1] and ids[i, j] < ids[i, j + 1])
                    for j in range(k - 1))
-    rng = np.random.default_rng(0)
-    start = int(rng.integers(0, ROWS - 200_000))
-    from oracle import fast
-    spot = fast.dense_scores(fast.synth_dense_bf16(1234, start, 200_000, 1024), qb[0])
-    inside = (ids[0] >= start) & (ids[0] < start + 200_000)
-    best_out = np.delete(spot, ids[0][inside] - start).max()
-    assert best_out <= sc[0, -1]
-    # stored rows are the generator's rows
-    assert np.array_equal(one.read_dense(int(tgt[0]), 1), _host_rows([tgt[0]]))
-
-    # ---- sparse: exact scores of the returned documents
-    ids_s, sc_s, cnt_s = one.search("sparse", k, qb, ip, tt, ww)
-    for i in range(nq):
-        docs = _host_docs(ids_s[i, :cnt_s[i]], thr, tables)
-        for j, (dt, dw) in enumerate(docs):
-            s, touched = oracle.sparse_scores(np.array([0, len(dt)]), dt, dw, tt[ip[i]:ip[i + 1]], ww[ip[i]:ip[i + 1]])
-            assert touched[0] and np.float32(sc_s[i, j]) == s[0]
-
-    # ---- hybrid: RRF of the two legs (top 2k each) reproduced on the host from the engine's own legs
     ids_h, sc_h, cnt_h = one.search("hybrid", k, qb, ip, tt, ww)
-    d20, _, _ = one.search("dense", 2 * k, qb)
-    s20, _, c20 = one.search("sparse", 2 * k, qb, ip, tt, ww)
-    for i in range(nq):
-        ei, es = oracle.rrf_fuse([d20[i], s20[i, :c20[i]]], k)
-        assert np.array_equal(ids_h[i, :cnt_h[i]], ei) and np.array_equal(sc_h[i, :cnt_h[i]], es)
 
     # ---- tcgen05 path == SIMT path
     one.set_dense_path(2)
@@ -122,6 +206,16 @@ def test_fullsize_properties(big):
     assert np.array_equal(h[:nq * k].reshape(nq, k), ids_h)
     assert np.array_equal(h[nq * k:2 * nq * k].view(np.float64).reshape(nq, k), sc_h)
     assert h[2 * nq * k:].view(np.int32)[nq] == 0
+
+    # ---- the same two halves as a shard GROUP (one process, worker threads): b200rag_group_search == single shard
+    from b200rag import ShardGroup
+    grp = ShardGroup([a, b])
+    gi, gs, gc = grp.search("hybrid", k, qb, ip, tt, ww)
+    assert np.array_equal(gi, ids_h) and np.array_equal(gs, sc_h) and np.array_equal(gc, cnt_h)
+    gi, gs, gc = grp.search("dense", 100, qb)
+    di, ds, dc = one.search("dense", 100, qb)
+    assert np.array_equal(gi, di) and np.array_equal(gs, ds) and np.array_equal(gc, dc)
+    grp.close()
 
 
 def test_fullsize_batched_paths_agree_with_single_query_paths(big):

@@ -269,7 +269,7 @@ def test_random_operation_sequences_match_reference_plugin():
 
 
 def test_save_load_host_logic(tmp_path):
-    """B200Retriever.save/load (payloads.jsonl, manifest.json, shard file) on the oracle-backed double: a restored
+    """B200Retriever.save/load (payload chunks, rows.npz, manifest.json, shard files) on the oracle-backed double: a restored
     retriever answers like the original one and like the reference plugin, keeps tombstones and schemas, refuses
     mismatching or corrupt directories."""
     from audio_rag.core import RetrievalError
@@ -287,9 +287,11 @@ def test_save_load_host_logic(tmp_path):
     d = str(tmp_path / "saved")
     ours.save(d)
     manifest = json.load(open(os.path.join(d, "manifest.json")))
-    assert manifest["rows"] == 210 and sum(manifest["alive"]) == 180
+    rows = np.load(os.path.join(d, "rows.npz"))
+    assert manifest["rows"] == 210 and int(rows["alive"].sum()) == 180 and len(rows["row_collection"]) == 210
     assert manifest["collections"]["legacy"]["hybrid"] is False and manifest["collections"]["dropped"]["exists"] is False
-    assert sum(1 for _ in open(os.path.join(d, "payloads.jsonl"), encoding="utf-8")) == 210
+    assert len(json.load(open(os.path.join(d, "payloads-0.json"), encoding="utf-8"))) == 210
+    assert not [f for f in os.listdir(d) if ".tmp-" in f], "every file is written under a temporary name and renamed"
 
     def fresh(dim=DIM):
         r = B200Retriever(RetrievalConfig(top_k=5), embedding_dim=dim)
@@ -297,7 +299,11 @@ def test_save_load_host_logic(tmp_path):
         return r
 
     back = fresh()
+    assert back.count("probe_only") == 0 and back.is_hybrid_collection("tenant_b") is False   # health probes register names
     back.load(d)
+    assert not back.collection_exists("probe_only") and back.is_hybrid_collection("tenant_b") is True, \
+        "load() replaces the registry: names registered before it must not alias saved collection ids"
+    assert sorted(back._coll_ids.values()) == list(range(len(back._coll_ids)))
     qs = make_queries(4, 21, 80, 11, E, S)
     _compare_all(ref, back, qs, ["tenant_a", "tenant_b", "legacy"], search_type="hybrid")
     _compare_all(ref, back, qs[:2], ["tenant_a"], search_type="dense", filter_metadata={"lang": "en"})
@@ -311,8 +317,8 @@ def test_save_load_host_logic(tmp_path):
         back.load(d)
     with pytest.raises(RetrievalError):
         fresh(dim=DIM * 2).load(d)
-    lines = open(os.path.join(d, "payloads.jsonl"), encoding="utf-8").readlines()
-    open(os.path.join(d, "payloads.jsonl"), "w", encoding="utf-8").writelines(lines[:-3])
+    block = json.load(open(os.path.join(d, "payloads-0.json"), encoding="utf-8"))
+    json.dump(block[:-3], open(os.path.join(d, "payloads-0.json"), "w", encoding="utf-8"))
     with pytest.raises(RetrievalError):
         fresh().load(d)
 
