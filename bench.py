@@ -15,6 +15,16 @@ re-score + RRF + top-k).  The corpus is FIXED at --rows (default 10M) and row-sh
   e2e         the same metric through the host-buffer call a plugin makes (`b200rag_search` at N=1, else
               `ShardedSearcher.search`): fp32 host query vectors + sparse CSR in pinned/pageable host memory ->
               normalise -> H2D -> kernels -> (all-gather) -> D2H of ids/scores, wall clock, max over ranks.
+  value_incl_copies
+              the same K steps with NOTHING pre-staged: every step copies its query batch from pinned host memory, runs
+              and reads its result back, all inside one CUDA event pair (SURVEY 8d's timing method).
+  e2e_plugin  (N = 1) wall clock through the reference-facing plugin call itself: `B200Retriever.search` with an
+              `EmbeddingResult` (Python lists) in and `RetrievalResult` objects out, the bench's shard adopted with
+              `attach_prebuilt`.
+  oracle_check
+              OUTSIDE the timed region: the hits of the last two e2e steps are compared with the CPU oracle run over
+              EVERY row of the corpus (each rank streams its shard's stored rows through oracle/oracle_c.c, the per-rank
+              leg lists are gathered and fused by the oracle); mismatches are summed over ranks.
   roofline    the dominant kernel (dense_scan): algorithmic bytes (rows_on_this_rank * dim * 2 per launch) / its mean
               launch duration, measured with CUDA events inside the timed region, / the measured HBM copy peak.
   cpu_baseline / --impl reference
@@ -66,11 +76,23 @@ def parse():
     return ap.parse_args()
 
 
-def workload(a):
+def workload(a, world=None):
+    """The `config` of BOTH arms (the reference arm reports on this arm's config): workload + how this arm runs it."""
+    world = a.gpus if world is None else world
+    per = -(-a.rows // world)
+    per = min(a.rows, -(-per // 8192) * 8192)
+    algo_gb = per * a.dim * 2 / 1e9
     return {"workload": f"{a.mode} dense(1024-d bf16 cosine)+sparse(Zipf BM25 impacts) RRF top-{a.top_k}, "
                         f"{a.rows} synthetic 256-token chunks, query batch {a.batch}",
             "corpus_rows": a.rows, "dim": a.dim, "batch": a.batch, "top_k": a.top_k, "search_type": a.mode,
-            "query_terms": a.query_tokens, "vocab": 250_002}
+            "query_terms": a.query_tokens, "vocab": 250_002, "rows_per_gpu": per,
+            "parallelism": (f"row-sharded x{world}, one process per GPU, per-shard candidates exchanged over NVLink "
+                            f"(CUDA-IPC peer windows, NCCL all-gather as fallback), merge/RRF kernel on every rank")
+            if world > 1 else "one shard on one GPU",
+            "l2": f"inputs larger than L2: {algo_gb:.2f} GB of corpus rows per GPU per step vs 126 MB L2; "
+                  f"a different query every step",
+            "timing": "one CUDA event pair around the K back-to-back steps on the launching stream (query "
+                      "batches pre-staged in HBM), max over ranks; p50/p95 from per-step event pairs"}
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
@@ -127,7 +149,23 @@ def cpu_reference(a, steps, warmup, sample_rows):
         blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
         blas_threads = os.cpu_count()
+    measured_10k = None
+    try:      # BASELINE config 1, the reference's own CPU-runnable case, MEASURED (no scaling): hybrid top-5 over 10k rows
+        n1 = min(10_000, n)
+        ref1 = oracle.RefShapedIndex(dense[:n1], ip[:n1 + 1], tt[:ip[n1]], ww[:ip[n1]])
+        t10 = []
+        for i in range(min(nq, 10)):
+            sl = slice(qi[i], qi[i + 1])
+            t0 = time.perf_counter()
+            ref1.hybrid(qf[i], qt[sl], qw[sl], None, 5)
+            t10.append(time.perf_counter() - t0)
+        measured_10k = {"rows": n1, "top_k": 5, "queries": len(t10), "ms_per_query": float(np.mean(t10) * 1e3),
+                        "queries_per_s": float(1.0 / np.mean(t10)), "scaled": False}
+    except Exception:
+        pass
     detail = {"value": qps, "unit": "queries/s", "cores": int(blas_threads), "kind": "port",
+              "measured_10k": measured_10k, "measured_ms_per_query_on_sample": per_query_sample * 1e3,
+              "sample_rows": n, "extrapolation_factor": scale,
               "sample": f"{len(times)} single hybrid queries over a {n}-row slice of the corpus "
                         f"({per_query_sample * 1e3:.1f} ms/query on the slice; BLAS sgemv uses {blas_threads} threads, "
                         f"the per-document sparse loop is single-threaded Python as in qdrant-client local mode), "
@@ -135,7 +173,7 @@ def cpu_reference(a, steps, warmup, sample_rows):
               "p50_ms_on_sample": float(np.median(times) * 1e3), "host_cpus": os.cpu_count(),
               "affinity_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
               "ms_on_sample_blas_1_thread": one_thread_ms}
-    return qps, detail, per_query_sample * scale * 1e3
+    return qps, detail, per_query_sample * 1e3
 
 
 def run_reference(a):
@@ -143,9 +181,12 @@ def run_reference(a):
     if rank != 0:
         return
     qps, detail, ms = cpu_reference(a, a.steps, a.warmup, a.cpu_sample_rows)
+    # one step = one query batch on the bounded SAMPLE (ms_per_step is what was really timed); `value` is that rate
+    # scaled linearly to the full corpus (cpu_baseline.extrapolation_factor), cpu_baseline.measured_10k is unscaled
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms * a.batch, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),
+            "ms_per_step_is": "measured on the bounded sample (cpu_baseline.sample_rows rows), not scaled",
             "cpu_baseline": detail,
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -163,7 +204,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -244,6 +285,88 @@ def build_shard(a, dev, lo, hi):
     torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()
     return sh
+
+
+
+def plugin_e2e(a, sh, qf, qi, qt, qw, steps, warmup, expect_last_ids, nsteps):
+    """Wall clock through the reference-facing plugin call: B200Retriever.search(EmbeddingResult) -> [RetrievalResult]."""
+    from b200rag.compat import EmbeddingResult, RetrievalConfig, SparseVector
+    from b200rag.retriever import B200Retriever
+    try:
+        conf = RetrievalConfig(qdrant_in_memory=True, top_k=a.top_k, search_type=a.mode)
+    except TypeError:
+        conf = RetrievalConfig(top_k=a.top_k, search_type=a.mode)
+    r = B200Retriever(conf, embedding_dim=a.dim)
+    r.attach_prebuilt([sh], "bench", hybrid=a.mode != "dense")
+    n = warmup + steps
+    first = max(0, nsteps * a.batch - n)                # the LAST queries of the run (the e2e loop ended on them)
+    embs = [EmbeddingResult(dense=[float(x) for x in qf[i]],
+                            sparse=SparseVector(indices=[int(t) for t in qt[qi[i]:qi[i + 1]]],
+                                                values=[float(w) for w in qw[qi[i]:qi[i + 1]]]))
+            for i in range(first, first + n)]
+    ts, res = [], None
+    for i, e in enumerate(embs):
+        t0 = time.perf_counter()
+        res = r.search(e, collection_name="bench")
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    out = {"value": len(ts) / float(np.sum(ts)), "unit": "queries/s", "p50_ms": float(np.median(ts) * 1e3),
+           "queries": len(ts), "api": "B200Retriever.search(EmbeddingResult lists) -> list[RetrievalResult]"}
+    if expect_last_ids is not None:
+        out["matches_c_abi_path"] = bool([int(x.chunk.text.split()[1]) for x in res] ==
+                                         [int(v) for v in expect_last_ids[0][:len(res)]])
+    r._shards = None                                    # the bench owns the shard
+    return out
+
+
+def oracle_check(a, sh, kept, step_arrays, world, rank, dev):
+    """The e2e hits of the last two steps against the oracle over ALL rows (tests/fullscale.py), mismatches summed."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from b200rag import normalize_bf16
+    from fullscale import LegJob, merge_topk, stream_oracle_legs
+    from oracle import oracle
+    t0 = time.time()
+    L = 2 * a.top_k if a.mode == "hybrid" else a.top_k
+    jobs, meta = [], []
+    for slot, ids, sc, cnt in kept:
+        f, ip, tt, ww = step_arrays(slot)
+        qb = normalize_bf16(f)
+        for b in range(min(a.batch, 2)):                # (bounded: the first two queries of a batch)
+            jobs.append(LegJob(qb[b] if a.mode != "sparse" else None,
+                               tt[ip[b]:ip[b + 1]] if a.mode != "dense" else None,
+                               ww[ip[b]:ip[b + 1]] if a.mode != "dense" else None, L=L))
+            meta.append((ids[b], sc[b], int(cnt[b])))
+    stream_oracle_legs(sh, jobs)
+    mine = [(j.dense, j.sparse) for j in jobs]
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    bad = 0
+    for q, (ids, sc, cnt) in enumerate(meta):
+        e = (np.zeros(0, np.int64), np.zeros(0, np.float32))
+        dl, sl = e, e
+        for r in range(world):
+            dl = merge_topk(dl, allr[r][q][0], L)
+            sl = merge_topk(sl, allr[r][q][1], L)
+        if a.mode == "hybrid":
+            ei, es = oracle.rrf_fuse([dl[0], sl[0]], a.top_k)
+        elif a.mode == "dense":
+            ei, es = dl[0], dl[1].astype(np.float64)
+        else:
+            ei, es = sl[0], sl[1].astype(np.float64)
+        ok = cnt == len(ei) and np.array_equal(ids[:cnt], ei) and np.array_equal(sc[:cnt], es)
+        bad += 0 if ok else 1
+    tot = torch.tensor([bad], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    return {"queries": len(meta), "mismatches": int(tot.item()), "ranks": world, "seconds": round(time.time() - t0, 2),
+            "what": "ids, counts and fp64 scores of the e2e results vs the CPU oracle scoring EVERY row of the corpus "
+                    "(each rank streams its shard's stored rows through oracle_c.c; leg lists gathered, fused by the oracle); "
+                    "mismatching queries summed over ranks"}
 
 
 def run_b200(a):
@@ -334,8 +457,24 @@ def run_b200(a):
     ids_dev, sc_dev, cnt_dev, amb = ss.fetch(b)
     sh.set_profiling(False)
 
+    # ------------------------------------------------------------------ (1b) the same steps with the copies inside
+    # nothing pre-staged: every step copies its (already normalised) query batch from host memory, runs, and reads its
+    # result back; ONE CUDA event pair around the K steps on the launching stream
+    pre_q = [(normalize_bf16(step_arrays(i % n_slots)[0]),) + tuple(step_arrays(i % n_slots)[1:]) for i in range(W, nsteps)]
+    barrier()
+    c_begin, c_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c_begin.record()
+    for qb_, ip_, tt_, ww_ in pre_q:
+        ss.stage(a.mode, a.top_k, qb_, ip_, tt_, ww_)
+        ss.fetch(ss.run_staged())
+    c_end.record()
+    barrier()
+    copies_ms = float(c_begin.elapsed_time(c_end))
+    del pre_q
+
     # ------------------------------------------------------------------ (2) end-to-end through the host-buffer call
     e2e_t = []
+    kept = []                                        # (step, ids, scores, counts) of the last two e2e steps -> oracle_check
     h2d = B * a.dim * 2 + (B + 1) * 8 + 0 + B * 8
     barrier()
     for i in range(nsteps):
@@ -351,6 +490,8 @@ def run_b200(a):
         if i >= W:
             e2e_t.append(time.perf_counter() - t0)
             h2d = max(h2d, B * a.dim * 2 + (B + 1) * 8 + len(tt) * 8 + B * 8)
+        if i >= nsteps - 2:
+            kept.append((i % n_slots, r_ids.copy(), r_sc.copy(), r_cnt.copy()))
     barrier()
     clocks = sampler.stop(t_load0, time.perf_counter()) if sampler else None   # both timed loops (device-resident + e2e)
     e2e_total = float(np.sum(e2e_t))
@@ -358,12 +499,27 @@ def run_b200(a):
     # the last e2e step and the last device-resident step used the same queries: results must agree
     same = bool(np.array_equal(r_ids, ids_dev) and np.array_equal(r_sc, sc_dev))
 
+    # ------------------------------------------------------------------ (3) through the plugin call itself (N = 1)
+    plugin = None
+    if world == 1:
+        try:
+            plugin = plugin_e2e(a, sh, qf, qi, qt, qw, min(K, 100), W, r_ids if B == 1 else None, nsteps)
+        except Exception as e:
+            plugin = {"value": None, "error": repr(e)}
+
+    # ------------------------------------------------------------------ (4) oracle check, outside every timed region
+    try:
+        ocheck = oracle_check(a, sh, kept, step_arrays, world, rank, dev)
+    except Exception as e:
+        ocheck = {"queries": 0, "mismatches": None, "error": repr(e)}
+
     # ------------------------------------------------------------------ reduce over ranks (MAX)
-    red = torch.tensor([total_ms, e2e_total, float(np.mean(dense_ms)), float(np.mean(sparse_ms)), wall_value],
+    red = torch.tensor([total_ms, e2e_total, float(np.mean(dense_ms)), float(np.mean(sparse_ms)), wall_value,
+                        copies_ms, float(np.mean(pre_ms)), float(np.mean(tail_ms))],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total, dense_k_ms, sparse_k_ms, wall_value = [float(x) for x in red.tolist()]
+    total_ms, e2e_total, dense_k_ms, sparse_k_ms, wall_value, copies_ms, pre_max, tail_max = [float(x) for x in red.tolist()]
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -414,26 +570,29 @@ def run_b200(a):
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {**workload(a), "rows_per_gpu": rows_rank,
-                       "parallelism": f"row-sharded x{world}, one process per GPU, per-shard candidates exchanged through "
-                                      f"{'CUDA-IPC peer windows (NVLink stores + flags)' if ss.p2p else 'an NCCL all-gather'}"
-                                      f", merge/RRF kernel on every rank" if world > 1 else "one shard on one GPU",
-                       "l2": f"inputs larger than L2: {algo_gb:.2f} GB of corpus rows per GPU per step vs 126 MB L2; "
-                             f"a different query every step",
-                       "timing": "one CUDA event pair around the K back-to-back steps on the launching stream (query "
-                                 "batches pre-staged in HBM), max over ranks; p50/p95 from per-step event pairs"},
+            "config": workload(a, world),
+            "exchange": ("CUDA-IPC peer windows (NVLink stores + epoch flags)" + (", pipelined tail" if ss.pipeline else "")
+                         if ss.p2p else "NCCL all-gather") if world > 1 else None,
             "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),
+            "value_incl_copies": {"value": B * K / (copies_ms / 1e3), "unit": "queries/s", "ms_per_step": copies_ms / K,
+                                  "note": "per step: H2D of the query batch + kernels + D2H of the result, one CUDA event "
+                                          "pair around the K steps, max over ranks"},
             "wall_ms_per_step_incl_staging": wall_value / K * 1e3,
             "e2e": {"value": B * K / e2e_total, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "p50_ms": float(np.median(e2e_t) * 1e3),
                     "api": "b200rag_search (C ABI, host buffers)" if world == 1 else
-                           "b200rag.dist.ShardedSearcher.search (host buffers; stage/legs/fuse C ABI + NCCL all-gather)",
+                           "b200rag.dist.ShardedSearcher.search (host buffers; stage/legs/exchange/fuse through the C ABI, "
+                           + ("candidates exchanged through CUDA-IPC peer windows)" if ss.p2p else "NCCL all-gather of the candidates)"),
                     "matches_device_path": same},
+            "e2e_plugin": plugin,
+            "oracle_check": ocheck,
             "gpu_launches": int(launches),
             "roofline": roof,
-            "step_breakdown_ms": {"launch_to_scan": float(np.mean(pre_ms)), "dense_scan": float(np.mean(dense_ms)),
-                                  "scan_end_to_fuse_end": float(np.mean(tail_ms)),
-                                  "note": "rank 0, CUDA events inside the timed steps"},
+            "step_breakdown_ms": {"launch_to_scan": pre_max, "dense_scan": dense_k_ms,
+                                  "scan_end_to_fuse_end": tail_max,
+                                  "rank0": {"launch_to_scan": float(np.mean(pre_ms)), "dense_scan": float(np.mean(dense_ms)),
+                                            "scan_end_to_fuse_end": float(np.mean(tail_ms))},
+                                  "note": "CUDA events inside the timed steps, mean over the steps, MAX over ranks"},
             "clocks": clocks,
             "build_s": t_build, "ambiguous_flags": int(amb),
         }

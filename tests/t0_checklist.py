@@ -338,6 +338,38 @@ def load_client(double: bool):
     return qdrant_client, models, version
 
 
+def probe() -> dict:
+    """Where a real ``qdrant_client`` was looked for and what was found (run on the GPU pod by
+    tests/test_oracle_vs_qdrant.py::test_t0_probe_on_gpu_pod, so the outcome is on record where a wheel could exist)."""
+    import glob
+    import importlib.util
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != FAKE_DIR]
+    searched = [os.path.join(ROOT, "baseline", "_ref")] + [p for p in sys.path if p]
+    for extra in (os.path.join(ROOT, "baseline", "_ref"),):
+        if os.path.isdir(extra) and extra not in sys.path:
+            sys.path.append(extra)
+    wheels = []
+    for d in ("/opt/wheelhouse", os.path.join(ROOT, "wheelhouse"), os.path.join(ROOT, "baseline"), "/root/wheelhouse", "/tmp"):
+        if os.path.isdir(d):
+            wheels += glob.glob(os.path.join(d, "qdrant*"))[:20] + glob.glob(os.path.join(d, "*", "qdrant*"))[:20]
+    out = {"python": sys.version.split()[0], "searched_sys_path": searched, "searched_wheel_dirs":
+           ["/opt/wheelhouse", "<repo>/wheelhouse", "<repo>/baseline", "/root/wheelhouse", "/tmp"], "wheels_found": wheels}
+    try:
+        spec = importlib.util.find_spec("qdrant_client")
+    except Exception as e:                      # a broken install can raise here
+        spec, out["find_spec_error"] = None, repr(e)
+    if spec is None:
+        out.update({"found": False, "error": "ModuleNotFoundError: No module named 'qdrant_client'"})
+        return out
+    try:
+        import qdrant_client  # noqa: F401
+        from importlib.metadata import version as _v
+        out.update({"found": True, "version": _v("qdrant-client"), "location": os.path.dirname(qdrant_client.__file__)})
+    except Exception as e:
+        out.update({"found": False, "error": repr(e)})
+    return out
+
+
 def run(double: bool) -> dict | None:
     loaded = load_client(double)
     if loaded is None:
@@ -351,6 +383,9 @@ def run(double: bool) -> dict | None:
 
 
 if __name__ == "__main__":
+    if "--probe" in sys.argv:
+        print(json.dumps(probe()))
+        sys.exit(0)
     rep = run(double="--double" in sys.argv)
     if rep is None:
         print("qdrant_client is not importable: oracle stays PARITY UNPINNED", file=sys.stderr)

@@ -21,11 +21,25 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
-    assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-9        # batch 1: q/s = 1 / step time
+    cbl = d["cpu_baseline"]
+    # ms_per_step is what was really timed (one query on the bounded sample); value = that rate scaled to the full corpus
+    assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] * cbl["extrapolation_factor"] / 1e3 - 1.0) < 1e-9
+    assert cbl["sample_rows"] == 1500 and abs(cbl["extrapolation_factor"] - 10_000_000 / 1500) < 1e-6
+    assert cbl["measured_10k"]["scaled"] is False and cbl["measured_10k"]["queries_per_s"] > 0
+    assert d["steps"] * d["ms_per_step"] / 1e3 < 60, "the timed region must fit inside the run"
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "1500-row slice" in cb["sample"]
     assert d["config"]["corpus_rows"] == 10_000_000 and d["config"]["top_k"] == 10 and "workload" in d["config"]
+    # the reference arm reports on the CUDA arm's config: same keys, same values
+    spec = importlib.util.spec_from_file_location("bench_mod_cfg", BENCH)
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+        assert d["config"] == bench.workload(bench.parse(), 1)
+    finally:
+        sys.argv = argv
 
 
 def test_reference_arm_other_ranks_exit_quietly():
