@@ -67,6 +67,8 @@ SYMBOLS = [
     ("b200rag_set_slack", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_exhaustive", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_exact_fallback", C.c_int, [_P, C.c_int32]),
+    ("b200rag_set_pipeline", C.c_int, [_P, C.c_int32, _P]),
+    ("b200rag_result_stream", C.c_void_p, [_P]),
     ("b200rag_set_dense_path", C.c_int, [_P, C.c_int32]),
     ("b200rag_debug_dense_scores", C.c_int, [_P, _P]),
     ("b200rag_sync", C.c_int, [_P]),
@@ -298,6 +300,16 @@ class Shard:
     def set_exact_fallback(self, on: bool):
         """Off: a search whose slack guard never clears raises B200RagError(ERR_INEXACT) instead of falling back."""
         check(self._lib.b200rag_set_exact_fallback(self._h, 1 if on else 0))
+
+    def set_pipeline(self, on: bool, stream_ptr: int = 0):
+        """Throughput mode for back-to-back staged searches: only the dense scan stays on the shard's stream, the tails,
+        the exchange and the fuse run on `result_stream()` -- `stream_ptr` (a cudaStream_t of the caller) or a stream of
+        the library's (see include/b200rag.h)."""
+        check(self._lib.b200rag_set_pipeline(self._h, 1 if on else 0, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def result_stream(self) -> int:
+        """cudaStream_t (as int) on which a search's fused results become available."""
+        return int(self._lib.b200rag_result_stream(self._h) or 0)
 
     def set_dense_path(self, path: int):
         """0 = auto, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM."""

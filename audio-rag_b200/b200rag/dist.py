@@ -62,14 +62,18 @@ class ShardedSearcher:
         if self.world > 1 and device.type == "cuda" and hasattr(shard, "p2p_export") and \
                 os.environ.get("B200RAG_P2P", "1") != "0":
             self._setup_p2p()
-        # Pipelined tail: exchange + fuse run on their own stream, so the NEXT search's scans start while this search
-        # still waits for its slowest peer (and while its fuse runs).  Candidate and result buffers are double-buffered
-        # per parity; a buffer is reused only after the fuse that read it has finished.  B200RAG_PIPELINE_TAIL=0/1.
-        self.pipeline = bool(self.p2p and os.environ.get("B200RAG_PIPELINE_TAIL", PIPELINE_TAIL_DEFAULT) == "1")
+        # Pipelined searches (b200rag_set_pipeline): only the dense scan of a search stays on the shard's stream; the
+        # sparse leg, both legs' tails, the exchange and the fuse run on the library's result stream, so the NEXT
+        # search's scan starts the moment this one's ends -- also while this search still waits for its slowest peer.
+        # Everything that touches the candidate and result buffers is on that one in-order stream, so single buffers
+        # suffice; results are read there (fetch / result_stream).  B200RAG_PIPELINE_TAIL=0/1.
+        self.pipeline = bool((self.p2p or self.world == 1) and device.type == "cuda" and hasattr(shard, "set_pipeline")
+                             and os.environ.get("B200RAG_PIPELINE_TAIL", PIPELINE_TAIL_DEFAULT) == "1")
         self._tail = None
         if self.pipeline:
+            # a torch-owned stream handed to the library (torch ops on a foreign stream would outlive it at teardown)
             self._tail = torch.cuda.Stream(device=device)
-            self.shard.p2p_set_stream(self._tail.cuda_stream)
+            self.shard.set_pipeline(True, self._tail.cuda_stream)
 
     def _setup_p2p(self):
         """Exchange CUDA IPC handles of the per-rank windows; every rank must succeed or all fall back to NCCL."""
@@ -111,13 +115,8 @@ class ShardedSearcher:
             b["host"] = torch.empty_like(b["out"], device="cpu")
             if self.device.type == "cuda":
                 b["host"] = b["host"].pin_memory()
-            if self.pipeline:
-                b["mine2"] = [b["mine"], torch.zeros_like(b["mine"])]
-                b["out2"] = [b["out"], torch.zeros_like(b["out"])]
-                b["legs_done"] = [torch.cuda.Event(), torch.cuda.Event()]
-                b["tail_done"] = [torch.cuda.Event(), torch.cuda.Event()]
-                b["used"] = [False, False]
-                b["n"] = 0
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()      # the zero fills precede any use on any stream
             self._bufs[key] = b
         return b
 
@@ -165,20 +164,13 @@ class ShardedSearcher:
         nlegs, B, L, k = self._cur
         b = self._buffers(nlegs, B, L, k)
         mine, allb, out = b["mine"], b["all"], b["out"]
-        if self.pipeline and mine.numel() * 8 <= self.p2p_slot_bytes:
-            par = b["n"] & 1
-            b["n"] += 1
-            mine, out = b["mine2"][par], b["out2"][par]
-            main = torch.cuda.current_stream(self.device)
-            if b["used"][par]:
-                main.wait_event(b["tail_done"][par])       # the fuse two searches ago has released this parity's buffers
-            self.shard.legs(mine, mine[-1])
-            b["legs_done"][par].record(main)
-            self._tail.wait_event(b["legs_done"][par])
-            self.shard.p2p_exchange(mine, mine.numel() * 8)              # (the library launches these two on the
-            self.shard.p2p_fuse(out[:B * k], out[B * k:2 * B * k], out[2 * B * k:])   #  tail stream: p2p_set_stream)
-            b["tail_done"][par].record(self._tail)
-            b["used"][par] = True
+        if self.pipeline and (self.world == 1 or mine.numel() * 8 <= self.p2p_slot_bytes):
+            self.shard.legs(mine, mine[-1])                # scan on the shard's stream, tails on the result stream
+            if self.world > 1:
+                self.shard.p2p_exchange(mine, mine.numel() * 8)          # (the library enqueues these on the result
+                self.shard.p2p_fuse(out[:B * k], out[B * k:2 * B * k], out[2 * B * k:])     #  stream, after the tails)
+            else:
+                self.shard.fuse(mine, 1, out[:B * k], out[B * k:2 * B * k], out[2 * B * k:], has_trailer=True)
             return {"out": out, "host": b["host"], "tail": True}
         self.shard.legs(mine, mine[-1])                    # (legs zeroes the trailer's ambiguity counter itself)
         if self.world > 1 and self.p2p and mine.numel() * 8 <= self.p2p_slot_bytes:
@@ -270,7 +262,8 @@ class ShardedSearcher:
         if self.world > 1 and self.device.type == "cuda" and hasattr(self.shard, "p2p_export") and \
                 os.environ.get("B200RAG_P2P", "1") != "0":
             self._setup_p2p()
-        if self.pipeline and not self.p2p:
+        if self.pipeline and not (self.p2p or self.world == 1):
             self.pipeline = False
-            self.shard.p2p_set_stream(0)
+            self.shard.set_pipeline(False)
+            self._tail = None
         self.broken = None

@@ -103,6 +103,13 @@ static int use_device(const Shard* s) {
     return B200RAG_OK;
 }
 
+// the shard's stream and, in pipelined mode, the side stream that carries the tails of the searches in flight
+static int sync_all(Shard* s) {
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->pipeline && s->pipe_stream != nullptr) B2_CUDA(cudaStreamSynchronize(s->pipe_stream));
+    return B200RAG_OK;
+}
+
 static int ensure_pinned(Shard* s, size_t bytes) {
     if (bytes <= s->h_pinned_cap) return B200RAG_OK;
     if (s->h_pinned != nullptr) { cudaStreamSynchronize(s->stream); cudaFreeHost(s->h_pinned); s->h_pinned = nullptr; }
@@ -172,6 +179,20 @@ static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t
 
 static int default_slack(int L) { return std::max(16, L / 2); }
 
+// Pipelined mode, classic-form fallbacks (tcgen05 batches, exhaustive legs, index rebuilds): the main stream first
+// waits until the side stream has finished the earlier searches' tails (they read buffers the classic form reuses) ...
+static int pipeline_drain(Shard* s) {
+    B2_CUDA(cudaEventRecord(s->ev_join, s->pipe_stream));
+    B2_CUDA(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+    return B200RAG_OK;
+}
+// ... and afterwards the side stream (where exchange and fuse are enqueued) waits for the legs the main stream ran
+static int pipeline_handover(Shard* s) {
+    B2_CUDA(cudaEventRecord(s->ev_fork, s->stream));
+    B2_CUDA(cudaStreamWaitEvent(s->pipe_stream, s->ev_fork, 0));
+    return B200RAG_OK;
+}
+
 static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     const b200rag_query& q = s->q;
     cudaStream_t st = s->stream;
@@ -184,13 +205,13 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
 
     B2_TRY(s->ws.thr.ensure((size_t)(B + 1) * 8, 0, st));
     s->ws.post_count.p = s->ws.thr.as<uint64_t>() + B;
-    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, st));
     B2_TRY(s->ws.exact.ensure((size_t)B * Lc * 8, 0, st));
 
     const bool want_dense = q.mode != B200RAG_SPARSE;
     const bool want_sparse = q.mode != B200RAG_DENSE;
     if (s->exhaustive) {
         // always-exact path: canonical score of every eligible row + full sort, no scan kernels, never ambiguous
+        if (s->pipeline) B2_TRY(pipeline_drain(s));
         s->stats.exhaustive = 1;
         b200rag_cand* o = cands;
         if (want_dense) {
@@ -202,15 +223,84 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) B2_CUDA(cudaMemsetAsync(o, 0, (size_t)B * L * sizeof(b200rag_cand), st));
             else B2_TRY(launch_exhaustive_leg(s, true, B, L, 0, 0.f, o));
         }
+        if (s->pipeline) B2_TRY(pipeline_handover(s));
         return B200RAG_OK;
     }
-    if (want_sparse && s->built_rows != s->n_rows) B2_TRY(build_inverted(s));
+    if (want_sparse && s->built_rows != s->n_rows) {
+        if (s->pipeline) B2_TRY(pipeline_drain(s));
+        B2_TRY(build_inverted(s));
+    }
 
     // Hybrid: the sparse leg (scan + fused tail) runs on the side stream while the dense scan streams the corpus.
     // The dense scan is issued FIRST so its persistent CTAs (1 per SM, 3-stage ring = 105 KB) are resident, and the
     // sparse CTAs (39 KB, 64 registers) co-reside with them.  Measured on B200: overlapped beats back-to-back at
     // 1.25M, 10M and 12.5M rows, top-10 and top-100 (10M: 3.26 vs 3.36 ms per search).
     const bool use_gemm_path = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
+
+    // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
+    const int nl_scan = dense_scan_nlists(s);
+    const bool piped = s->pipeline && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
+                       leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B), Lc));
+    if (piped) {
+        cudaStream_t sd = s->pipe_stream;
+        const int par = (int)(s->legs_calls & 1);                 // (legs_calls was incremented by the caller)
+        DevBuf& lists = par ? s->ws.lists_b : s->ws.lists_a;      // the dense tail two calls ago has released this set
+        b200rag_cand* out_dense = cands;
+        b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
+        const bool sparse_live = want_sparse && s->nnz > 0 && s->staged_q_terms > 0;
+        int nlists = 0;
+        if (want_dense) {
+            B2_TRY(lists.ensure((size_t)B * nl_scan * Lc * 8, 0, st));
+            if (s->ev_tail_rec[par]) B2_CUDA(cudaStreamWaitEvent(st, s->ev_tail[par], 0));
+            B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)B * 8, st));
+        }
+        B2_CUDA(cudaEventRecord(s->ev_fork, st));                  // side-stream work of this search starts after this point
+        B2_CUDA(cudaStreamWaitEvent(sd, s->ev_fork, 0));
+        if (ambiguous != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous, 0, 4, sd));
+        if (want_dense) {
+            s->dense_stage_cap = s->dense_stage_cap_env;
+            const int rc = launch_dense_scan(s, B, Lc, lists.as<uint64_t>(), &nlists);
+            s->dense_stage_cap = 0;
+            if (rc != B200RAG_OK) return rc;
+            B2_CUDA(cudaEventRecord(s->ev_scan[par], st));
+        }
+        s->stream = sd;                                            // the launchers below enqueue on s->stream
+        int rc = B200RAG_OK;
+        if (want_sparse) {
+            if (!sparse_live) {
+                cudaError_t e = cudaMemsetAsync(out_sparse, 0, (size_t)B * L * sizeof(b200rag_cand), sd);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(sparse leg)");
+            } else {
+                const int sp_lists = sparse_scan_nlists(s, B);
+                rc = s->ws.lists_c.ensure((size_t)B * sp_lists * Lc * 8, 0, sd);
+                if (rc == B200RAG_OK) rc = s->ws.q_eps.ensure((size_t)B * 8, 0, sd);
+                if (rc == B200RAG_OK) {
+                    cudaError_t e = cudaMemsetAsync(s->ws.q_eps.as<int32_t>() + B, 0x80, (size_t)B * 4, sd);
+                    if (e == cudaSuccess) e = cudaMemsetAsync(s->ws.post_count.p, 0, 8, sd);
+                    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(sparse thresholds)");
+                }
+                if (rc == B200RAG_OK) rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.q_eps.as<float>(), s->ws.q_eps.as<int>() + B);
+                if (rc == B200RAG_OK) rc = launch_leg_tail(s, true, B, sp_lists, Lc, L, s->ws.lists_c.as<uint64_t>(), 1e-12f, 2e-6f,
+                                                           s->ws.q_eps.as<float>(), 0, 0.f, out_sparse, ambiguous);
+            }
+        }
+        if (rc == B200RAG_OK && want_dense) {
+            cudaError_t e = cudaStreamWaitEvent(sd, s->ev_scan[par], 0);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent(scan)");
+            const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
+            if (rc == B200RAG_OK) rc = launch_leg_tail(s, false, B, nlists, Lc, L, lists.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
+                                                       q.score_threshold, out_dense, ambiguous);
+            if (rc == B200RAG_OK) {
+                e = cudaEventRecord(s->ev_tail[par], sd);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord(tail)"); else s->ev_tail_rec[par] = true;
+            }
+        }
+        s->stream = st;
+        return rc;
+    }
+    if (s->pipeline) B2_TRY(pipeline_drain(s));     // classic form below: the side stream's earlier searches must be through
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, st));
+
     // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
     // nothing could co-reside.  The FILTER epilogue keeps no per-query state (96 registers); with one pipeline stage
     // less it leaves room for a sparse CTA per SM, and the two legs overlap like in the single-query case.
@@ -299,6 +389,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         B2_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
         B2_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     }
+    if (s->pipeline) B2_TRY(pipeline_handover(s));
     (void)nlegs;
     return B200RAG_OK;
 }
@@ -462,6 +553,8 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     if (s == nullptr) return;
     cudaSetDevice(s->cfg.device);
     cudaStreamSynchronize(s->stream);
+    if (s->side_stream) cudaStreamSynchronize(s->side_stream);
+    if (s->pipeline && s->pipe_stream) cudaStreamSynchronize(s->pipe_stream);
     p2p_release(s);
     s->dense.release(); s->row_ids.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
     s->ws.ex_keys.release(); s->ws.ex_sorted.release(); s->ws.ex_temp.release();
@@ -476,6 +569,10 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     for (int r = 0; r < kProfileRing; ++r)
         for (int i = 0; i < 6; ++i)
             if (s->ev_ring[r][i]) cudaEventDestroy(s->ev_ring[r][i]);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_scan[i]) cudaEventDestroy(s->ev_scan[i]);
+        if (s->ev_tail[i]) cudaEventDestroy(s->ev_tail[i]);
+    }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -487,7 +584,7 @@ int b200rag_set_stream(b200rag_shard* sp, void* stream) {
     Shard* s = (Shard*)sp;
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
-    B2_CUDA(cudaStreamSynchronize(s->stream));
+    B2_TRY(sync_all(s));
     s->stream = (cudaStream_t)stream;  // NULL == the legacy default stream
     return B200RAG_OK;
 }
@@ -511,6 +608,33 @@ int b200rag_set_exact_fallback(b200rag_shard* sp, int32_t on) {
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     s->exact_fallback = on != 0;
     return B200RAG_OK;
+}
+
+int b200rag_set_pipeline(b200rag_shard* sp, int32_t on, void* stream) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    cudaStream_t second = stream != nullptr ? (cudaStream_t)stream : s->side_stream;
+    if (on && second == nullptr) { set_error("set_pipeline: no second stream available"); return B200RAG_ERR_STATE; }
+    if (on && second == s->stream) { set_error("set_pipeline: the second stream must differ from the shard's stream"); return B200RAG_ERR_INVALID; }
+    B2_TRY(sync_all(s));
+    if (s->side_stream != nullptr) B2_CUDA(cudaStreamSynchronize(s->side_stream));
+    if (on && s->ev_scan[0] == nullptr)
+        for (int i = 0; i < 2; ++i) {
+            B2_CUDA(cudaEventCreateWithFlags(&s->ev_scan[i], cudaEventDisableTiming));
+            B2_CUDA(cudaEventCreateWithFlags(&s->ev_tail[i], cudaEventDisableTiming));
+        }
+    s->ev_tail_rec[0] = s->ev_tail_rec[1] = false;
+    s->pipeline = on != 0 ? 1 : 0;
+    s->pipe_stream = s->pipeline ? second : nullptr;
+    s->x_stream = s->pipe_stream;                            // exchange + fuse follow the tails
+    return B200RAG_OK;
+}
+
+void* b200rag_result_stream(const b200rag_shard* sp) {
+    const Shard* s = (const Shard*)sp;
+    if (s == nullptr) return nullptr;
+    return (void*)(s->x_stream != nullptr ? s->x_stream : s->stream);
 }
 
 int b200rag_set_dense_path(b200rag_shard* sp, int32_t path) {
@@ -541,8 +665,7 @@ int b200rag_sync(b200rag_shard* sp) {
     Shard* s = (Shard*)sp;
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
-    B2_CUDA(cudaStreamSynchronize(s->stream));
-    return B200RAG_OK;
+    return sync_all(s);
 }
 
 int b200rag_add(b200rag_shard* sp, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
@@ -639,7 +762,7 @@ int b200rag_clear(b200rag_shard* sp) {
     Shard* s = (Shard*)sp;
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
-    B2_CUDA(cudaStreamSynchronize(s->stream));
+    B2_TRY(sync_all(s));
     s->n_rows = 0; s->nnz = 0; s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0;
     s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->last_id = INT64_MIN;
@@ -702,6 +825,7 @@ static int mask_store(Shard* s, int32_t id, const uint32_t* words, int64_t n_row
     const size_t words_in = (size_t)((n_rows + 31) / 32);
     for (auto& sl : s->slots) sl.staged = false;     // staged batches hold raw mask pointers
     s->staged = false;
+    B2_TRY(sync_all(s));                             // no search in flight may still read the mask being replaced
     DevBuf& b = s->masks[id];
     B2_TRY(b.ensure(words_total * 4, 0, s->stream));
     B2_CUDA(cudaMemsetAsync(b.p, 0, b.cap, s->stream));
@@ -726,7 +850,7 @@ int b200rag_mask_drop(b200rag_shard* sp, int32_t id) {
     auto it = s->masks.find(id);
     if (it == s->masks.end()) return B200RAG_OK;
     use_device(s);
-    cudaStreamSynchronize(s->stream);
+    sync_all(s);
     for (auto& sl : s->slots) sl.staged = false;
     s->staged = false;
     it->second.release();
@@ -842,8 +966,9 @@ static int stage_impl(b200rag_shard* sp, const b200rag_query* q, int32_t slot, b
     QuerySlot& sl = s->slots[(size_t)slot];
     sl.staged = false;
     B2_TRY(sl.buf.ensure(total, 0, s->stream));
-    // the previous batch's H2D must have drained before the pinned block is rewritten
-    B2_CUDA(cudaStreamSynchronize(s->stream));
+    // the previous batch's H2D must have drained before the pinned block is rewritten (pipelined mode: a search in
+    // flight on the side stream may still read the slot's device block, too)
+    B2_TRY(sync_all(s));
     uint8_t* h = (uint8_t*)s->h_pinned;
     uint8_t* d = sl.buf.as<uint8_t>();
     if (need_dense && !dev) memcpy(h + o_bits, q->q_dense_bits, (size_t)B * s->dim * 2);
@@ -909,7 +1034,8 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     ++s->legs_calls;
     s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[4], s->stream)); s->ev_in = true; }
-    if (ambiguous_dev != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));   // callers need not pre-zero it
+    // callers need not pre-zero the counter (pipelined mode: the legs zero it on the stream their tails run on)
+    if (ambiguous_dev != nullptr && !s->pipeline) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
 
@@ -923,10 +1049,15 @@ int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int3
     if (!s->staged) { set_error("fuse: no staged query batch"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
     const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
-    B2_TRY(launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
-                       has_trailer, out_ids, out_scores, out_counts));
-    if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[5], s->stream)); s->ev_out = true; }
-    return B200RAG_OK;
+    cudaStream_t keep = s->stream;
+    if (s->x_stream != nullptr) s->stream = s->x_stream;       // pipelined mode: the fuse follows the tails
+    int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
+                         has_trailer, out_ids, out_scores, out_counts);
+    if (rc == B200RAG_OK && s->profile) {
+        if (cudaEventRecord(s->ev[5], s->stream) == cudaSuccess) s->ev_out = true; else rc = cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    }
+    s->stream = keep;
+    return rc;
 }
 
 int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, double* out_scores,
@@ -937,6 +1068,10 @@ int b200rag_search(b200rag_shard* sp, const b200rag_query* q, int64_t* out_ids, 
         return B200RAG_ERR_INVALID;
     }
     B2_TRY(b200rag_stage(sp, q));
+    // the synchronous host-buffer call gains nothing from the pipelined form: it runs the classic one
+    const int saved_pipeline = s->pipeline;
+    if (saved_pipeline) { B2_TRY(sync_all(s)); s->pipeline = 0; }
+    struct PipeRestore { Shard* s; int v; ~PipeRestore() { s->pipeline = v; } } pipe_restore{s, saved_pipeline};
     cudaStream_t st = s->stream;
     const int B = s->q.batch, K = s->q.top_k;
     const int nlegs = s->q.mode == B200RAG_HYBRID ? 2 : 1;
@@ -1237,12 +1372,12 @@ int b200rag_get_stats(const b200rag_shard* sp, b200rag_stats* out) {
     if (s->ws.post_count.p != nullptr && s->staged) {
         // not on the timed path: read the postings counter the last sparse scan accumulated
         unsigned long long v = 0;
-        if (cudaSetDevice(s->cfg.device) == cudaSuccess &&
+        if (cudaSetDevice(s->cfg.device) == cudaSuccess && sync_all(s) == B200RAG_OK &&
             cudaMemcpyAsync(&v, s->ws.post_count.p, 8, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
             cudaStreamSynchronize(s->stream) == cudaSuccess)
             s->stats.sparse_postings = (int64_t)v;
     }
-    if (s->profile && (s->ev_dense || s->ev_sparse) && cudaStreamSynchronize(s->stream) == cudaSuccess) {
+    if (s->profile && (s->ev_dense || s->ev_sparse) && sync_all(s) == B200RAG_OK) {
         float ms = 0.f;
         if (s->ev_dense && cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) s->stats.dense_scan_ms = ms;
         if (s->ev_sparse && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) s->stats.sparse_scan_ms = ms;
@@ -1259,7 +1394,7 @@ int b200rag_get_stats_step(const b200rag_shard* sp, int32_t steps_back, b200rag_
     Shard* s = (Shard*)sp;
     *out = b200rag_stats{};
     if (!s->profile || s->legs_calls <= steps_back) { set_error("get_stats_step: profiling is off or no such call"); return B200RAG_ERR_STATE; }
-    if (cudaSetDevice(s->cfg.device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "get_stats_step");
+    if (cudaSetDevice(s->cfg.device) != cudaSuccess || sync_all(s) != B200RAG_OK) return cuda_fail(cudaGetLastError(), "get_stats_step");
     const int64_t call = s->legs_calls - 1 - steps_back;
     cudaEvent_t* ev = s->ev_ring[call % kProfileRing];
     bool f[4];

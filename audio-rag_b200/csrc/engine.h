@@ -129,6 +129,13 @@ struct Shard {
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
+    // Pipelined mode (b200rag_set_pipeline): ONLY the dense scan runs on `stream`; the sparse leg, both legs' tails,
+    // exchange and fuse run on `side_stream`, so the next search's scan starts the moment this one's ends.  Candidate
+    // lists are double-buffered per call parity and ordered with ev_scan / ev_tail.
+    int pipeline = 0;
+    cudaStream_t pipe_stream = nullptr;   // the second stream of pipelined mode: the caller's, or side_stream
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
+    bool ev_tail_rec[2] = {false, false};
     bool exhaustive = false;      // legs score EVERY eligible row canonically and sort (always exact; exact.cu)
     bool exact_fallback = true;   // b200rag_search falls back to the exhaustive pass when the slack guard never clears
 

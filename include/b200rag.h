@@ -108,6 +108,17 @@ int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximat
  *                          (default 1; the environment variable B200RAG_EXACT_FALLBACK=0 sets the default to 0). */
 int b200rag_set_exhaustive(b200rag_shard* s, int32_t on);
 int b200rag_set_exact_fallback(b200rag_shard* s, int32_t on);
+/* Pipelined searches (throughput mode for callers that enqueue search after search on staged batches: b200rag_legs ->
+ * [b200rag_p2p_exchange ->] b200rag_fuse / b200rag_p2p_fuse, no host synchronisation in between).  With pipeline on, ONLY
+ * the dense scan of a search runs on the shard's stream; the sparse leg, both legs' merge + exact re-score + finalize,
+ * the candidate exchange and the fuse run on an internal second stream, so the next search's scan starts the moment
+ * this one's ends (candidate lists are double-buffered, ordering is by CUDA events inside the library).  Results of a
+ * search are complete on b200rag_result_stream(): enqueue or synchronise dependent work THERE (everything that writes
+ * or reads the caller's candidate / output buffers runs on that one in-order stream, so single buffers suffice).
+ * `second_stream`: a cudaStream_t of the caller to use as that second stream (it must outlive the pipelined mode), or
+ * NULL for a stream the library owns.  b200rag_search (synchronous, host buffers) always runs the classic form. */
+int b200rag_set_pipeline(b200rag_shard* s, int32_t on, void* second_stream);
+void* b200rag_result_stream(const b200rag_shard* s); /* cudaStream_t on which fused results become available */
 /* Dense kernel choice: 0 = auto (bulk-copy SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT scan,
  * 2 = tcgen05 GEMM.  Both produce bit-identical results (candidates are re-scored in the canonical order). */
 int b200rag_set_dense_path(b200rag_shard* s, int32_t path);

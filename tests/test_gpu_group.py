@@ -179,3 +179,58 @@ def test_integration_md_snippet_verbatim(gpu):
             e_i, e_s = oracle_search(c, "hybrid", q_bits[q], sp_terms, sp_weights, None, 10)
             assert_result_equal(ids[0], scores[0], int(counts[0]), e_i, e_s, ctx=f"INTEGRATION.md snippet, query {q}")
     shard.close()
+
+
+def test_pipelined_searches_back_to_back(gpu, monkeypatch):
+    """Pipelined mode (b200rag_set_pipeline through ShardedSearcher): 90 staged searches enqueued back to back with NO
+    host synchronisation -- single queries (pipelined form: scan on the shard's stream, tails + fuse on the result
+    stream, double-buffered candidate lists) interleaved with batches of 4 (tcgen05 path: classic form inside the
+    pipeline, drain + hand-over) and sparse-only / dense-only searches.  Every step's fused output is copied aside on the
+    result stream and compared with the oracle afterwards: a missing event or a reused buffer shows up as a stale or
+    torn result."""
+    import torch
+    from b200rag import Shard, normalize_bf16
+    from b200rag.dist import ShardedSearcher
+    monkeypatch.setenv("B200RAG_PIPELINE_TAIL", "1")
+    c = Corpus(50_000, dim=1024, vocab=60_013)
+    dev = torch.device("cuda", gpu)
+    sh = Shard(dim=1024, vocab=c.vocab, device=gpu, docs_per_block=2048)
+    sh.add(c.bits, c.indptr, c.terms, c.w)
+    ss = ShardedSearcher(sh, dev)
+    assert ss.pipeline and ss.result_stream() is not None
+    nst, k = 90, 10
+    plan = []                                            # (mode, first query, batch)
+    qn = 0
+    for i in range(nst):
+        mode = ("hybrid", "hybrid", "dense", "hybrid", "sparse")[i % 5]
+        B = 4 if i % 7 == 3 else 1
+        plan.append((mode, qn, B))
+        qn += B
+    qf, ip, tt, ww = c.queries(qn, qid_start=300)
+    qb = normalize_bf16(qf)
+    for i, (mode, q0, B) in enumerate(plan):
+        ss.stage(mode, k, qb[q0:q0 + B], ip[q0:q0 + B + 1] - ip[q0], tt[ip[q0]:ip[q0 + B]], ww[ip[q0]:ip[q0 + B]], slot=i)
+    keep = []
+    for i in range(nst):
+        ss.use_slot(i)
+        b = ss.run_staged()
+        with torch.cuda.stream(ss.result_stream()):
+            keep.append(b["out"].clone())
+    torch.cuda.synchronize(dev)
+    for i, (mode, q0, B) in enumerate(plan):
+        h = keep[i].cpu().numpy()
+        ids = h[:B * k].reshape(B, k)
+        sc = h[B * k:2 * B * k].view(np.float64).reshape(B, k)
+        cnt = h[2 * B * k:].view(np.int32)
+        assert cnt[B] == 0 and cnt[B + 1] == 0
+        for b_ in range(B):
+            q = q0 + b_
+            e_i, e_s = oracle_search(c, mode, qb[q], tt[ip[q]:ip[q + 1]], ww[ip[q]:ip[q + 1]], None, k)
+            assert_result_equal(ids[b_], sc[b_], int(cnt[b_]), e_i, e_s, ctx=f"pipelined step {i} ({mode}, B={B}) q{b_}")
+    # the synchronous host-buffer call still works on a pipelined shard (classic form), and so does a retry-free search()
+    r = ss.search("hybrid", k, qb[:1], ip[:2], tt[:ip[1]], ww[:ip[1]])
+    e_i, e_s = oracle_search(c, "hybrid", qb[0], tt[:ip[1]], ww[:ip[1]], None, k)
+    assert_result_equal(r[0][0], r[1][0], int(r[2][0]), e_i, e_s, ctx="search() on a pipelined searcher")
+    r = sh.search("hybrid", k, qb[:1], ip[:2], tt[:ip[1]], ww[:ip[1]])
+    assert_result_equal(r[0][0], r[1][0], int(r[2][0]), e_i, e_s, ctx="b200rag_search on a pipelined shard")
+    sh.close()

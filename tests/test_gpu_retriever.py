@@ -102,7 +102,7 @@ def test_save_load_round_trip(gpu, tmp_path):
     before = snapshot(r)
     d = str(tmp_path / "idx")
     r.save(d)
-    assert sorted(os.listdir(d)) == ["manifest.json", "payloads.jsonl", "shard.bin"]
+    assert sorted(os.listdir(d)) == ["manifest.json", "payloads-0.json", "rows.npz", "shard-0.bin"]
     r2 = _retriever(gpu, top_k=6)
     r2.load(d)
     assert snapshot(r2) == before
@@ -115,9 +115,12 @@ def test_save_load_round_trip(gpu, tmp_path):
     assert snapshot(r2) == snapshot(r)
     # a foreign file is refused
     from b200rag.compat import RetrievalError
-    open(os.path.join(d, "shard.bin"), "wb").write(b"not a shard file at all")
+    open(os.path.join(d, "shard-0.bin"), "wb").write(b"not a shard file at all")
     r3 = _retriever(gpu, top_k=6)
     with pytest.raises(RetrievalError):
         r3.load(d)
+    # ... and leaves a clean, usable retriever behind (a failed load must not corrupt later adds)
+    r3.add(ch, em, "fresh")
+    assert r3.count("fresh") == 40 and len(r3.search(qs[0], collection_name="fresh", search_type="hybrid")) == 6
     for x in (r, r2, r3):
         x.close()
