@@ -352,10 +352,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 // phase A: one compare per score against my query's threshold (registers only)
                 uint32_t cm = 0;
                 if (active) {
-                    const int nvalid = p.n_rows - row0 < 32 ? (int)(p.n_rows - row0) : 32;
+                    // one compare + one bit-insert per score; rows beyond the shard's end (last tile only) and ineligible
+                    // rows are cut from the whole 32-bit word afterwards
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        cm |= ((__uint_as_float(v[j]) + 0.0f >= thr_s) && j < nvalid) ? (1u << j) : 0u;
+                        cm |= (__uint_as_float(v[j]) >= thr_s) ? (1u << j) : 0u;
+                    const int64_t left = p.n_rows - row0;
+                    if (left < 32) cm &= left > 0 ? ((1u << (int)left) - 1u) : 0u;
                     if (mask != nullptr) cm &= __ldg(mask + tt * (kGemmN / 32) + c);
                 }
                 if (!__any_sync(0xffffffffu, cm != 0)) continue;

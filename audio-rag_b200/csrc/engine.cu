@@ -240,7 +240,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
     const int nl_scan = dense_scan_nlists(s);
     const bool piped = s->pipeline && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
-                       leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B), Lc));
+                       leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
     if (piped) {
         cudaStream_t sd = s->pipe_stream;
         const int par = (int)(s->legs_calls & 1);                 // (legs_calls was incremented by the caller)
@@ -271,7 +271,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
                 cudaError_t e = cudaMemsetAsync(out_sparse, 0, (size_t)B * L * sizeof(b200rag_cand), sd);
                 if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(sparse leg)");
             } else {
-                const int sp_lists = sparse_scan_nlists(s, B);
+                const int sp_lists = sparse_scan_nlists(s, B, Lc);
                 rc = s->ws.lists_c.ensure((size_t)B * sp_lists * Lc * 8, 0, sd);
                 if (rc == B200RAG_OK) rc = s->ws.q_eps.ensure((size_t)B * 8, 0, sd);
                 if (rc == B200RAG_OK) {
@@ -363,7 +363,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) {
             B2_CUDA(cudaMemsetAsync(out, 0, (size_t)B * L * sizeof(b200rag_cand), sst));
         } else {
-            const int sp_lists = sparse_scan_nlists(s, B);
+            const int sp_lists = sparse_scan_nlists(s, B, Lc);
             const size_t need = (size_t)B * sp_lists * Lc * 8;
             B2_TRY(s->ws.lists_c.ensure(need, 0, st));
             B2_TRY(s->ws.lists_d.ensure(need, 0, st));
@@ -1147,23 +1147,58 @@ struct ShardFileHeader {
     int64_t n_rows, nnz;
 };
 
-static int dev_to_file(Shard* s, const void* dev, size_t bytes, FILE* f, void* stage, size_t stage_bytes) {
-    for (size_t o = 0; o < bytes; o += stage_bytes) {
-        const size_t n = std::min(stage_bytes, bytes - o);
-        B2_CUDA(cudaMemcpyAsync(stage, (const uint8_t*)dev + o, n, cudaMemcpyDeviceToHost, s->stream));
-        B2_CUDA(cudaStreamSynchronize(s->stream));
-        if (fwrite(stage, 1, n, f) != n) { set_error("save: short write"); return B200RAG_ERR_INVALID; }
+// Two pinned staging halves: the copy engine fills / drains one half while the host writes / reads the other, so disk and
+// PCIe overlap (one event per half; nothing waits for a whole chunk round trip).
+struct StagePair {
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+    int init(size_t half_bytes) {
+        bytes = half_bytes;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaMallocHost(&buf[i], half_bytes) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return B200RAG_ERR_CUDA;
+            }
+        }
+        return B200RAG_OK;
+    }
+    ~StagePair() {
+        for (int i = 0; i < 2; ++i) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+    }
+};
+
+static int dev_to_file(Shard* s, const void* dev, size_t bytes, FILE* f, StagePair& sp) {
+    const size_t nchunks = (bytes + sp.bytes - 1) / sp.bytes;
+    auto len = [&](size_t c) { return std::min(sp.bytes, bytes - c * sp.bytes); };
+    if (nchunks > 0) {
+        B2_CUDA(cudaMemcpyAsync(sp.buf[0], dev, len(0), cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaEventRecord(sp.ev[0], s->stream));
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {      // next chunk travels while this one is written
+            B2_CUDA(cudaMemcpyAsync(sp.buf[(c + 1) & 1], (const uint8_t*)dev + (c + 1) * sp.bytes, len(c + 1), cudaMemcpyDeviceToHost, s->stream));
+            B2_CUDA(cudaEventRecord(sp.ev[(c + 1) & 1], s->stream));
+        }
+        B2_CUDA(cudaEventSynchronize(sp.ev[c & 1]));
+        if (fwrite(sp.buf[c & 1], 1, len(c), f) != len(c)) { set_error("save: short write"); return B200RAG_ERR_INVALID; }
     }
     return B200RAG_OK;
 }
 
-static int file_to_dev(Shard* s, void* dev, size_t bytes, FILE* f, void* stage, size_t stage_bytes) {
-    for (size_t o = 0; o < bytes; o += stage_bytes) {
-        const size_t n = std::min(stage_bytes, bytes - o);
-        if (fread(stage, 1, n, f) != n) { set_error("load: file is truncated"); return B200RAG_ERR_INVALID; }
-        B2_CUDA(cudaMemcpyAsync((uint8_t*)dev + o, stage, n, cudaMemcpyHostToDevice, s->stream));
-        B2_CUDA(cudaStreamSynchronize(s->stream));
+static int file_to_dev(Shard* s, void* dev, size_t bytes, FILE* f, StagePair& sp) {
+    const size_t nchunks = (bytes + sp.bytes - 1) / sp.bytes;
+    auto len = [&](size_t c) { return std::min(sp.bytes, bytes - c * sp.bytes); };
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (c >= 2) B2_CUDA(cudaEventSynchronize(sp.ev[c & 1]));      // the copy that last used this half has drained
+        if (fread(sp.buf[c & 1], 1, len(c), f) != len(c)) { set_error("load: file is truncated"); cudaStreamSynchronize(s->stream); return B200RAG_ERR_INVALID; }
+        B2_CUDA(cudaMemcpyAsync((uint8_t*)dev + c * sp.bytes, sp.buf[c & 1], len(c), cudaMemcpyHostToDevice, s->stream));
+        B2_CUDA(cudaEventRecord(sp.ev[c & 1], s->stream));
     }
+    B2_CUDA(cudaStreamSynchronize(s->stream));
     return B200RAG_OK;
 }
 
@@ -1177,17 +1212,15 @@ extern "C" int b200rag_save(b200rag_shard* sp, const char* path) {
     ShardFileHeader h{};
     memcpy(h.magic, "B200RAG1", 8);
     h.version = 2; h.dim = s->dim; h.vocab = s->vocab; h.n_rows = s->n_rows; h.nnz = s->nnz;
-    const size_t stage_bytes = (size_t)64 << 20;
-    void* stage = nullptr;
+    StagePair stage;
     int rc = B200RAG_OK;
-    if (cudaMallocHost(&stage, stage_bytes) != cudaSuccess) { cudaGetLastError(); fclose(f); set_error("save: no pinned staging memory"); return B200RAG_ERR_CUDA; }
+    if (stage.init((size_t)32 << 20) != B200RAG_OK) { fclose(f); set_error("save: no pinned staging memory"); return B200RAG_ERR_CUDA; }
     if (fwrite(&h, sizeof(h), 1, f) != 1) { set_error("save: short write"); rc = B200RAG_ERR_INVALID; }
-    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->dense.p, (size_t)s->n_rows * s->dim * 2, f, stage, stage_bytes);
-    if (rc == B200RAG_OK) rc = dev_to_file(s, s->fwd_ptr.p, (size_t)(s->n_rows + 1) * 8, f, stage, stage_bytes);
-    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_terms.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
-    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_w.p, (size_t)s->nnz * 4, f, stage, stage_bytes);
-    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->row_ids.p, (size_t)s->n_rows * 8, f, stage, stage_bytes);
-    cudaFreeHost(stage);
+    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->dense.p, (size_t)s->n_rows * s->dim * 2, f, stage);
+    if (rc == B200RAG_OK) rc = dev_to_file(s, s->fwd_ptr.p, (size_t)(s->n_rows + 1) * 8, f, stage);
+    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_terms.p, (size_t)s->nnz * 4, f, stage);
+    if (rc == B200RAG_OK && s->nnz > 0) rc = dev_to_file(s, s->fwd_w.p, (size_t)s->nnz * 4, f, stage);
+    if (rc == B200RAG_OK && s->n_rows > 0) rc = dev_to_file(s, s->row_ids.p, (size_t)s->n_rows * 8, f, stage);
     if (fclose(f) != 0 && rc == B200RAG_OK) { set_error("save: close failed"); rc = B200RAG_ERR_INVALID; }
     return rc;
 }
@@ -1206,22 +1239,21 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
     if (h.dim != s->dim || h.vocab != s->vocab || h.n_rows < 0 || h.nnz < 0 || h.n_rows > 0xFFFFFFF0ll) {
         fclose(f); set_error("load: file was written for another dim/vocab"); return B200RAG_ERR_INVALID;
     }
-    const size_t stage_bytes = (size_t)64 << 20;
-    void* stage = nullptr;
-    if (cudaMallocHost(&stage, stage_bytes) != cudaSuccess) { cudaGetLastError(); fclose(f); set_error("load: no pinned staging memory"); return B200RAG_ERR_CUDA; }
+    StagePair stage;
+    if (stage.init((size_t)32 << 20) != B200RAG_OK) { fclose(f); set_error("load: no pinned staging memory"); return B200RAG_ERR_CUDA; }
     cudaStream_t st = s->stream;
     int rc = s->dense.ensure((size_t)std::max<int64_t>(h.n_rows, 1) * s->dim * 2, 0, st);
     if (rc == B200RAG_OK) rc = s->fwd_ptr.ensure((size_t)(h.n_rows + 1) * 8, 0, st);
     if (rc == B200RAG_OK) rc = s->fwd_terms.ensure((size_t)(h.nnz + 1) * 4, 0, st);
     if (rc == B200RAG_OK) rc = s->fwd_w.ensure((size_t)(h.nnz + 1) * 4, 0, st);
-    if (rc == B200RAG_OK && h.n_rows > 0) rc = file_to_dev(s, s->dense.p, (size_t)h.n_rows * s->dim * 2, f, stage, stage_bytes);
-    if (rc == B200RAG_OK) rc = file_to_dev(s, s->fwd_ptr.p, (size_t)(h.n_rows + 1) * 8, f, stage, stage_bytes);
-    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_terms.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
-    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_w.p, (size_t)h.nnz * 4, f, stage, stage_bytes);
+    if (rc == B200RAG_OK && h.n_rows > 0) rc = file_to_dev(s, s->dense.p, (size_t)h.n_rows * s->dim * 2, f, stage);
+    if (rc == B200RAG_OK) rc = file_to_dev(s, s->fwd_ptr.p, (size_t)(h.n_rows + 1) * 8, f, stage);
+    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_terms.p, (size_t)h.nnz * 4, f, stage);
+    if (rc == B200RAG_OK && h.nnz > 0) rc = file_to_dev(s, s->fwd_w.p, (size_t)h.nnz * 4, f, stage);
     if (rc == B200RAG_OK) rc = s->row_ids.ensure((size_t)std::max<int64_t>(h.n_rows, 1) * 8, 0, st);
     int64_t last_id = INT64_MIN;
     if (rc == B200RAG_OK && h.n_rows > 0) {
-        if (h.version >= 2) rc = file_to_dev(s, s->row_ids.p, (size_t)h.n_rows * 8, f, stage, stage_bytes);
+        if (h.version >= 2) rc = file_to_dev(s, s->row_ids.p, (size_t)h.n_rows * 8, f, stage);
         else rc = launch_fill_row_ids(s, s->row_ids.as<int64_t>(), s->cfg.row_base, h.n_rows);
         if (rc == B200RAG_OK) {
             cudaError_t e = cudaMemcpyAsync(&last_id, s->row_ids.as<int64_t>() + (h.n_rows - 1), 8, cudaMemcpyDeviceToHost, st);
@@ -1229,7 +1261,6 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
             if (e != cudaSuccess) rc = cuda_fail(e, "load: row ids");
         }
     }
-    cudaFreeHost(stage);
     fclose(f);
     if (rc != B200RAG_OK) {
         // leave a clean empty shard behind: the forward index's first word is what append_rows builds on

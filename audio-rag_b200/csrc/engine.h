@@ -57,6 +57,7 @@ constexpr int kSparseThreads = 256;
 constexpr int kMaxQueryTermsChunk = 256;
 constexpr int kMergeMaxKeys = 8192;    // smem bound of one merge group
 constexpr int kMergeGroupKeys = 1024;  // preferred group size (keeps the bitonic network short)
+constexpr int kTailMaxKeys = 65536;    // most candidate keys (n_lists * Lc) the fused leg tail takes in one launch
 
 struct DevPtr {
     void* p = nullptr;
@@ -250,7 +251,7 @@ int launch_fill_row_ids(Shard* s, int64_t* dst, int64_t first_id, int64_t n);
 int build_inverted(Shard* s);
 int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, float* q_eps /*[batch]*/,
                        int* gthr /*[batch], preset to INT_MIN*/);
-int sparse_scan_nlists(const Shard* s, int batch);
+int sparse_scan_nlists(const Shard* s, int batch, int Lc);
 
 // ---- synth.cu ------------------------------------------------------------------------------------------
 int launch_synth_dense(cudaStream_t st, uint64_t seed, int64_t row0, int64_t n, int dim, uint16_t* out);

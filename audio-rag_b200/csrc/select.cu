@@ -246,7 +246,7 @@ int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* appr
 //      or above it, so only those survivors (typically a few Lc) are compacted and bitonic-sorted
 //   2. the best Lc are re-scored exactly, one warp per candidate (same canonical order as the standalone kernels)
 //   3. exact keys are sorted, thresholded, guarded and emitted exactly like finalize_leg_kernel
-constexpr int kTailMaxKeys = 65536;     // the lists stay in global memory (two strided passes); only survivors go to smem
+// (kTailMaxKeys, engine.h: the lists stay in global memory -- two strided passes; only survivors go to smem)
 constexpr int kTailSurvivorCap = 4096;
 
 __device__ __forceinline__ uint64_t rescore_dense_warp(const uint16_t* __restrict__ corpus, int dim,

@@ -434,16 +434,26 @@ static int launch_scan_nt(Shard* s, const SparseScanParams& p, int batch) {
 }
 
 // blocks per CTA: as many as possible (the running threshold prunes better) while the grid still has ~4 waves of CTAs
-int sparse_scan_bpc(const Shard* s, int batch) {
+// ... and, for large top-k, enough blocks per CTA that the leg's n_lists * Lc candidate keys still fit the fused tail
+// (one launch instead of merge tree + re-score + finalize: at 12.5M rows, top-100, 1 526 lists x 300 keys took the slow
+// path and the leg's tail cost 0.36 ms; 7 blocks per CTA give 218 lists, and the longer scan hides behind the dense one)
+int sparse_scan_bpc(const Shard* s, int batch, int Lc) {
     if (s->sparse_bpc > 0) return s->sparse_bpc;
     const int64_t items = (int64_t)s->n_blocks * batch;
     int64_t bpc = items / ((int64_t)4 * s->sm_count * 8);
     if (bpc < 1) bpc = 1;
+    if (Lc > 0 && s->fused_tail) {
+        const int64_t max_lists = kTailMaxKeys / Lc;
+        if (max_lists >= 1) {
+            const int64_t need = (s->n_blocks + max_lists - 1) / max_lists;
+            if (need > bpc && need <= 32) bpc = need;
+        }
+    }
     if (bpc > 32) bpc = 32;
     return (int)bpc;
 }
-int sparse_scan_nlists(const Shard* s, int batch) {
-    const int bpc = sparse_scan_bpc(s, batch);
+int sparse_scan_nlists(const Shard* s, int batch, int Lc) {
+    const int bpc = sparse_scan_bpc(s, batch, Lc);
     return (int)((s->n_blocks + bpc - 1) / bpc);
 }
 
@@ -463,8 +473,8 @@ int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, float* 
     p.out = out_lists;
     p.Lc = Lc;
     p.n_blocks = (int)s->n_blocks;
-    p.bpc = sparse_scan_bpc(s, batch);
-    p.n_groups = sparse_scan_nlists(s, batch);
+    p.bpc = sparse_scan_bpc(s, batch, Lc);
+    p.n_groups = sparse_scan_nlists(s, batch, Lc);
     p.sel_cap = next_pow2(2 * Lc) < 512 ? 512 : next_pow2(2 * Lc);
     p.w_absmax = s->w_absmax;
     p.q_eps = q_eps;
