@@ -69,6 +69,7 @@ SYMBOLS = [
     ("b200rag_set_exact_fallback", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_pipeline", C.c_int, [_P, C.c_int32, _P]),
     ("b200rag_result_stream", C.c_void_p, [_P]),
+    ("b200rag_pipeline_pause", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_dense_path", C.c_int, [_P, C.c_int32]),
     ("b200rag_debug_dense_scores", C.c_int, [_P, _P]),
     ("b200rag_sync", C.c_int, [_P]),
@@ -306,6 +307,10 @@ class Shard:
         the exchange and the fuse run on `result_stream()` -- `stream_ptr` (a cudaStream_t of the caller) or a stream of
         the library's (see include/b200rag.h)."""
         check(self._lib.b200rag_set_pipeline(self._h, 1 if on else 0, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def pipeline_pause(self, on: bool):
+        """Classic-form searches on a pipelined shard (no CUDA call; see include/b200rag.h)."""
+        check(self._lib.b200rag_pipeline_pause(self._h, 1 if on else 0))
 
     def result_stream(self) -> int:
         """cudaStream_t (as int) on which a search's fused results become available."""

@@ -26,7 +26,7 @@ import torch.distributed as dist
 from ._ffi import Shard
 
 
-PIPELINE_TAIL_DEFAULT = "0"
+PIPELINE_TAIL_DEFAULT = "1"
 
 
 def shard_bounds(n_total: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
@@ -70,6 +70,7 @@ class ShardedSearcher:
         self.pipeline = bool((self.p2p or self.world == 1) and device.type == "cuda" and hasattr(shard, "set_pipeline")
                              and os.environ.get("B200RAG_PIPELINE_TAIL", PIPELINE_TAIL_DEFAULT) == "1")
         self._tail = None
+        self._paused = False
         if self.pipeline:
             # a torch-owned stream handed to the library (torch ops on a foreign stream would outlive it at teardown)
             self._tail = torch.cuda.Stream(device=device)
@@ -164,7 +165,7 @@ class ShardedSearcher:
         nlegs, B, L, k = self._cur
         b = self._buffers(nlegs, B, L, k)
         mine, allb, out = b["mine"], b["all"], b["out"]
-        if self.pipeline and (self.world == 1 or mine.numel() * 8 <= self.p2p_slot_bytes):
+        if self.pipeline and not self._paused and (self.world == 1 or mine.numel() * 8 <= self.p2p_slot_bytes):
             self.shard.legs(mine, mine[-1])                # scan on the shard's stream, tails on the result stream
             if self.world > 1:
                 self.shard.p2p_exchange(mine, mine.numel() * 8)          # (the library enqueues these on the result
@@ -219,6 +220,9 @@ class ShardedSearcher:
                                     rrf_k)
         slack0 = None
         exhaustive = False
+        if self.pipeline:                 # a lone synchronous search: classic form, everything on the shard's stream
+            self._paused = True
+            self.shard.pipeline_pause(True)
         try:
             for attempt in range(max_retries + 2):
                 ids, scores, counts, amb = self.fetch(self.run_staged())
@@ -245,6 +249,9 @@ class ShardedSearcher:
                 self.shard.set_slack(0)
             if exhaustive:
                 self.shard.set_exhaustive(False)
+            if self._paused:
+                self._paused = False
+                self.shard.pipeline_pause(False)
         return ids, scores, counts
 
     def reset(self):

@@ -223,7 +223,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) B2_CUDA(cudaMemsetAsync(o, 0, (size_t)B * L * sizeof(b200rag_cand), st));
             else B2_TRY(launch_exhaustive_leg(s, true, B, L, 0, 0.f, o));
         }
-        if (s->pipeline) B2_TRY(pipeline_handover(s));
+        if (s->pipeline && !s->pipeline_paused) B2_TRY(pipeline_handover(s));
         return B200RAG_OK;
     }
     if (want_sparse && s->built_rows != s->n_rows) {
@@ -239,7 +239,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
 
     // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
     const int nl_scan = dense_scan_nlists(s);
-    const bool piped = s->pipeline && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
+    const bool piped = s->pipeline && !s->pipeline_paused && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
                        leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
     if (piped) {
         cudaStream_t sd = s->pipe_stream;
@@ -389,7 +389,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         B2_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
         B2_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     }
-    if (s->pipeline) B2_TRY(pipeline_handover(s));
+    if (s->pipeline && !s->pipeline_paused) B2_TRY(pipeline_handover(s));
     (void)nlegs;
     return B200RAG_OK;
 }
@@ -631,10 +631,17 @@ int b200rag_set_pipeline(b200rag_shard* sp, int32_t on, void* stream) {
     return B200RAG_OK;
 }
 
+int b200rag_pipeline_pause(b200rag_shard* sp, int32_t on) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    s->pipeline_paused = on != 0;
+    return B200RAG_OK;
+}
+
 void* b200rag_result_stream(const b200rag_shard* sp) {
     const Shard* s = (const Shard*)sp;
     if (s == nullptr) return nullptr;
-    return (void*)(s->x_stream != nullptr ? s->x_stream : s->stream);
+    return (void*)(s->x_stream != nullptr && !s->pipeline_paused ? s->x_stream : s->stream);
 }
 
 int b200rag_set_dense_path(b200rag_shard* sp, int32_t path) {
@@ -1035,7 +1042,10 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[4], s->stream)); s->ev_in = true; }
     // callers need not pre-zero the counter (pipelined mode: the legs zero it on the stream their tails run on)
-    if (ambiguous_dev != nullptr && !s->pipeline) B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));
+    if (ambiguous_dev != nullptr && (!s->pipeline || s->pipeline_paused)) {
+        if (s->pipeline) B2_TRY(pipeline_drain(s));        // (paused: earlier pipelined searches may still use the counter)
+        B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));
+    }
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
 
@@ -1050,7 +1060,7 @@ int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int3
     B2_TRY(use_device(s));
     const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr) s->stream = s->x_stream;       // pipelined mode: the fuse follows the tails
+    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;       // pipelined mode: the fuse follows the tails
     int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
                          has_trailer, out_ids, out_scores, out_counts);
     if (rc == B200RAG_OK && s->profile) {
@@ -1351,7 +1361,7 @@ int b200rag_p2p_exchange(b200rag_shard* sp, const void* mine, int64_t nbytes) {
     B2_TRY(use_device(s));
     ++s->x_epoch;
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr) s->stream = s->x_stream;
+    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;
     const int rc = launch_exchange(s, mine, nbytes, s->ws.xpeers_dev.as<void*>(), s->x_world, s->x_rank, s->x_slot_bytes,
                                    (int)(s->x_epoch & 1ull), s->x_epoch);
     s->stream = keep;
@@ -1378,7 +1388,7 @@ int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, in
     const b200rag_cand* gathered = (const b200rag_cand*)(win + (size_t)(s->x_epoch & 1ull) * s->x_world * s->x_slot_bytes);
     const unsigned long long* flags = (const unsigned long long*)(win + (size_t)2 * s->x_world * s->x_slot_bytes);
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr) s->stream = s->x_stream;
+    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;
     int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
                          out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch);
     if (rc == B200RAG_OK && s->profile) {

@@ -134,6 +134,7 @@ struct Shard {
     // exchange and fuse run on `side_stream`, so the next search's scan starts the moment this one's ends.  Candidate
     // lists are double-buffered per call parity and ordered with ev_scan / ev_tail.
     int pipeline = 0;
+    bool pipeline_paused = false;         // pipelined mode stays set up, but searches take the classic form on `stream`
     cudaStream_t pipe_stream = nullptr;   // the second stream of pipelined mode: the caller's, or side_stream
     cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
     bool ev_tail_rec[2] = {false, false};

@@ -113,6 +113,38 @@ int launch_rescore_dense(Shard* s, int batch, int64_t Lc, const uint64_t* approx
     return B200RAG_OK;
 }
 
+// Exact sparse score of one document against one chunk of query terms (<= kMaxQueryTermsChunk, ascending, in shared
+// memory), by one warp.  The DOCUMENT's terms are streamed with coalesced loads (~200 per 256-token chunk: 6 rounds) and
+// each is looked up in the query chunk by binary search in shared memory -- one global round trip instead of a chain of
+// dependent global loads per query term.  Products land in prod[j] (j = position of the term in the query), lane 0 then
+// adds them in ascending j = ascending term index: the canonical order of SURVEY R3, bit-equal to the oracle.
+__device__ __forceinline__ void sparse_exact_chunk(int64_t ds, int64_t de, const uint32_t* __restrict__ fwd_terms,
+                                                   const float* __restrict__ fwd_w, const uint32_t* qt, const float* qw,
+                                                   int cn, double* prod, uint8_t* present, int lane, double& acc,
+                                                   int& touched) {
+    for (int j = lane; j < cn; j += 32) present[j] = 0;
+    __syncwarp();
+    const uint32_t tlo = qt[0], thi = qt[cn - 1];
+    for (int64_t i = ds + lane; i < de; i += 32) {
+        const uint32_t t = fwd_terms[i];
+        if (t < tlo || t > thi) continue;
+        int lo = 0, hi = cn;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (qt[mid] < t) lo = mid + 1; else hi = mid;
+        }
+        if (lo < cn && qt[lo] == t) {
+            present[lo] = 1;
+            prod[lo] = __dmul_rn((double)qw[lo], (double)fwd_w[i]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int j = 0; j < cn; ++j)
+            if (present[j]) { acc = __dadd_rn(acc, prod[j]); touched = 1; }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ exact sparse
 __global__ void __launch_bounds__(256) rescore_sparse_kernel(const int64_t* __restrict__ fwd_ptr,
                                                              const uint32_t* __restrict__ fwd_terms,
@@ -143,24 +175,7 @@ __global__ void __launch_bounds__(256) rescore_sparse_kernel(const int64_t* __re
         __syncthreads();
         for (int j = threadIdx.x; j < cn; j += blockDim.x) { qt[j] = q_terms[c0 + j]; qw[j] = q_w[c0 + j]; }
         __syncthreads();
-        if (active) {
-            for (int j = lane; j < cn; j += 32) {
-                const uint32_t t = qt[j];
-                int64_t lo = ds, hi = de;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (fwd_terms[mid] < t) lo = mid + 1; else hi = mid;
-                }
-                const bool hit = lo < de && fwd_terms[lo] == t;
-                present[w][j] = hit ? 1 : 0;
-                if (hit) prod[w][j] = __dmul_rn((double)qw[j], (double)fwd_w[lo]);
-            }
-            __syncwarp();
-            if (lane == 0)
-                for (int j = 0; j < cn; ++j)
-                    if (present[w][j]) { acc = __dadd_rn(acc, prod[w][j]); touched = 1; }
-            __syncwarp();
-        }
+        if (active) sparse_exact_chunk(ds, de, fwd_terms, fwd_w, qt, qw, cn, prod[w], present[w], lane, acc, touched);
     }
     if (i < Lc && lane == 0)
         exact[(size_t)q * Lc + i] = (active && (touched || !drop_untouched)) ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
@@ -415,22 +430,8 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
                 for (int j = tid; j < cn; j += NT) { qt[j] = p.q_terms[c0 + j]; qw[j] = p.q_w[c0 + j]; }
                 __syncthreads();
                 if (active) {
-                    for (int j = lane; j < cn; j += 32) {
-                        const uint32_t t = qt[j];
-                        int64_t lo = ds, hi = de;
-                        while (lo < hi) {
-                            const int64_t mid = (lo + hi) >> 1;
-                            if (p.fwd_terms[mid] < t) lo = mid + 1; else hi = mid;
-                        }
-                        const bool hit = lo < de && p.fwd_terms[lo] == t;
-                        present[warp][j] = hit ? 1 : 0;
-                        if (hit) prod[warp][j] = __dmul_rn((double)qw[j], (double)p.fwd_w[lo]);
-                    }
-                    __syncwarp();
-                    if (lane == 0)
-                        for (int j = 0; j < cn; ++j)
-                            if (present[warp][j]) acc = __dadd_rn(acc, prod[warp][j]);
-                    __syncwarp();
+                    int touched = 0;
+                    sparse_exact_chunk(ds, de, p.fwd_terms, p.fwd_w, qt, qw, cn, prod[warp], present[warp], lane, acc, touched);
                 }
             }
             if (i < p.Lc && lane == 0) tkeys[i] = active ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;

@@ -119,6 +119,11 @@ int b200rag_set_exact_fallback(b200rag_shard* s, int32_t on);
  * NULL for a stream the library owns.  b200rag_search (synchronous, host buffers) always runs the classic form. */
 int b200rag_set_pipeline(b200rag_shard* s, int32_t on, void* second_stream);
 void* b200rag_result_stream(const b200rag_shard* s); /* cudaStream_t on which fused results become available */
+/* While paused, a pipelined shard runs its searches in the classic form, everything on the shard's stream (the first
+ * such search waits, on the device, for the pipelined ones still in flight).  No CUDA call, no synchronisation: a caller
+ * that mixes a stream of pipelined searches with an occasional synchronous one (ShardedSearcher.search) brackets the
+ * latter with pause(1) / pause(0) -- a lone search is ~10-50 us faster without the stream hand-overs. */
+int b200rag_pipeline_pause(b200rag_shard* s, int32_t on);
 /* Dense kernel choice: 0 = auto (bulk-copy SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT scan,
  * 2 = tcgen05 GEMM.  Both produce bit-identical results (candidates are re-scored in the canonical order). */
 int b200rag_set_dense_path(b200rag_shard* s, int32_t path);
