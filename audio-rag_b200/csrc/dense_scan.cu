@@ -368,7 +368,7 @@ int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nli
         p.q_bits = s->ws.q_bits.as<uint16_t>() + (size_t)q * s->dim;
         p.masks[0] = s->h_masks.empty() ? nullptr : s->h_masks[q];
         p.masks[1] = (nq == 2 && !s->h_masks.empty()) ? s->h_masks[q + 1] : nullptr;
-        p.g_thr = s->ws.thr.as<uint64_t>() + q;
+        p.g_thr = s->ws.thr.as<uint64_t>() + (size_t)s->thr_par * batch + q;
         p.out = out_lists + (size_t)q * grid * Lc;
         p.out_q_stride = (int64_t)grid * Lc;
         p.Lc = Lc;

@@ -179,6 +179,17 @@ static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t
 
 static int default_slack(int L) { return std::max(16, L / 2); }
 
+// per-query side arrays of the sparse leg inside ws.q_eps: [B] u64 grid-wide threshold keys | [B] f32 error bounds of
+// the approximate scores | [B] i32 grid-wide thresholds in fixed-point units
+struct SparseAux { uint64_t* gkey; float* eps; int* gthr; };
+static SparseAux sparse_aux(Shard* s, int B) {
+    SparseAux a;
+    a.gkey = s->ws.q_eps.as<uint64_t>();
+    a.eps = reinterpret_cast<float*>(a.gkey + B);
+    a.gthr = reinterpret_cast<int*>(a.eps + B);
+    return a;
+}
+
 // Pipelined mode, classic-form fallbacks (tcgen05 batches, exhaustive legs, index rebuilds): the main stream first
 // waits until the side stream has finished the earlier searches' tails (they read buffers the classic form reuses) ...
 static int pipeline_drain(Shard* s) {
@@ -203,8 +214,10 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     int Lc = L + slack;
     if (Lc > 3 * B200RAG_MAX_TOPK) Lc = 3 * B200RAG_MAX_TOPK;
 
-    B2_TRY(s->ws.thr.ensure((size_t)(B + 1) * 8, 0, st));
-    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + B;
+    // thr: [2][B] grid-wide dense thresholds (one set per call parity: in pipelined mode the previous search's tail
+    // still reads its set while this search's scan raises the other) | [1] postings counter
+    B2_TRY(s->ws.thr.ensure((size_t)(2 * B + 1) * 8, 0, st));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 2 * B;
     B2_TRY(s->ws.exact.ensure((size_t)B * Lc * 8, 0, st));
 
     const bool want_dense = q.mode != B200RAG_SPARSE;
@@ -252,14 +265,16 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         if (want_dense) {
             B2_TRY(lists.ensure((size_t)B * nl_scan * Lc * 8, 0, st));
             if (s->ev_tail_rec[par]) B2_CUDA(cudaStreamWaitEvent(st, s->ev_tail[par], 0));
-            B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)B * 8, st));
+            B2_CUDA(cudaMemsetAsync(s->ws.thr.as<uint64_t>() + (size_t)par * B, 0, (size_t)B * 8, st));
         }
         B2_CUDA(cudaEventRecord(s->ev_fork, st));                  // side-stream work of this search starts after this point
         B2_CUDA(cudaStreamWaitEvent(sd, s->ev_fork, 0));
         if (ambiguous != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous, 0, 4, sd));
         if (want_dense) {
             s->dense_stage_cap = s->dense_stage_cap_env;
+            s->thr_par = par;
             const int rc = launch_dense_scan(s, B, Lc, lists.as<uint64_t>(), &nlists);
+            s->thr_par = 0;
             s->dense_stage_cap = 0;
             if (rc != B200RAG_OK) return rc;
             B2_CUDA(cudaEventRecord(s->ev_scan[par], st));
@@ -273,15 +288,17 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             } else {
                 const int sp_lists = sparse_scan_nlists(s, B, Lc);
                 rc = s->ws.lists_c.ensure((size_t)B * sp_lists * Lc * 8, 0, sd);
-                if (rc == B200RAG_OK) rc = s->ws.q_eps.ensure((size_t)B * 8, 0, sd);
+                if (rc == B200RAG_OK) rc = s->ws.q_eps.ensure((size_t)B * 16, 0, sd);
+                SparseAux aux = sparse_aux(s, B);
                 if (rc == B200RAG_OK) {
-                    cudaError_t e = cudaMemsetAsync(s->ws.q_eps.as<int32_t>() + B, 0x80, (size_t)B * 4, sd);
+                    cudaError_t e = cudaMemsetAsync(aux.gkey, 0, (size_t)B * 8, sd);
+                    if (e == cudaSuccess) e = cudaMemsetAsync(aux.gthr, 0x80, (size_t)B * 4, sd);
                     if (e == cudaSuccess) e = cudaMemsetAsync(s->ws.post_count.p, 0, 8, sd);
                     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(sparse thresholds)");
                 }
-                if (rc == B200RAG_OK) rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.q_eps.as<float>(), s->ws.q_eps.as<int>() + B);
+                if (rc == B200RAG_OK) rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), aux.eps, aux.gthr, aux.gkey);
                 if (rc == B200RAG_OK) rc = launch_leg_tail(s, true, B, sp_lists, Lc, L, s->ws.lists_c.as<uint64_t>(), 1e-12f, 2e-6f,
-                                                           s->ws.q_eps.as<float>(), 0, 0.f, out_sparse, ambiguous);
+                                                           aux.eps, 0, 0.f, out_sparse, ambiguous, aux.gkey);
             }
         }
         if (rc == B200RAG_OK && want_dense) {
@@ -289,7 +306,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent(scan)");
             const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
             if (rc == B200RAG_OK) rc = launch_leg_tail(s, false, B, nlists, Lc, L, lists.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
-                                                       q.score_threshold, out_dense, ambiguous);
+                                                       q.score_threshold, out_dense, ambiguous,
+                                                       s->ws.thr.as<uint64_t>() + (size_t)par * B);
             if (rc == B200RAG_OK) {
                 e = cudaEventRecord(s->ev_tail[par], sd);
                 if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord(tail)"); else s->ev_tail_rec[par] = true;
@@ -299,7 +317,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         return rc;
     }
     if (s->pipeline) B2_TRY(pipeline_drain(s));     // classic form below: the side stream's earlier searches must be through
-    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, st));
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(2 * B + 1) * 8, st));
 
     // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
     // nothing could co-reside.  The FILTER epilogue keeps no per-query state (96 registers); with one pipeline stage
@@ -349,7 +367,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
             if (approx == nullptr) {
                 B2_TRY(launch_leg_tail(s, false, B, nlists, Lc, L, s->ws.lists_a.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
-                                       q.score_threshold, out, ambiguous));
+                                       q.score_threshold, out, ambiguous, s->ws.thr.as<uint64_t>()));
             } else {
                 B2_TRY(launch_rescore_dense(s, B, Lc, approx, s->ws.exact.as<uint64_t>()));
                 B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
@@ -368,18 +386,20 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_TRY(s->ws.lists_c.ensure(need, 0, st));
             B2_TRY(s->ws.lists_d.ensure(need, 0, st));
             B2_TRY(s->ws.exact2.ensure((size_t)B * Lc * 8, 0, st));
-            B2_TRY(s->ws.q_eps.ensure((size_t)B * 8, 0, st));
-            B2_CUDA(cudaMemsetAsync(s->ws.q_eps.as<int32_t>() + B, 0x80, (size_t)B * 4, sst));   // thresholds: 0x80808080 < any score
+            B2_TRY(s->ws.q_eps.ensure((size_t)B * 16, 0, st));
+            const SparseAux aux = sparse_aux(s, B);
+            B2_CUDA(cudaMemsetAsync(aux.gkey, 0, (size_t)B * 8, sst));
+            B2_CUDA(cudaMemsetAsync(aux.gthr, 0x80, (size_t)B * 4, sst));   // thresholds: 0x80808080 < any score
             s->stream = sst;                                   // the launchers below enqueue on s->stream
-            int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.q_eps.as<float>(), s->ws.q_eps.as<int>() + B);
+            int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), aux.eps, aux.gthr, aux.gkey);
             if (s->fused_tail && leg_tail_fits(sp_lists, Lc)) {
                 if (rc == B200RAG_OK) rc = launch_leg_tail(s, true, B, sp_lists, Lc, L, s->ws.lists_c.as<uint64_t>(), 1e-12f, 2e-6f,
-                                                           s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
+                                                           aux.eps, 0, 0.f, out, ambiguous, aux.gkey);
             } else {
                 uint64_t* approx = nullptr;
                 if (rc == B200RAG_OK) rc = launch_merge_tree(s, B, sp_lists, Lc, s->ws.lists_c.as<uint64_t>(), s->ws.lists_d.as<uint64_t>(), &approx);
                 if (rc == B200RAG_OK) rc = launch_rescore_sparse(s, B, Lc, approx, s->ws.exact2.as<uint64_t>());
-                if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, s->ws.q_eps.as<float>(), 0, 0.f, out, ambiguous);
+                if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, aux.eps, 0, 0.f, out, ambiguous);
             }
             s->stream = st;
             if (rc != B200RAG_OK) return rc;
@@ -658,9 +678,9 @@ int b200rag_debug_dense_scores(b200rag_shard* sp, float* out_scores_dev) {
     if (s->n_rows == 0) return B200RAG_OK;
     B2_TRY(use_device(s));
     const int B = s->q.batch, Lc = 16;
-    B2_TRY(s->ws.thr.ensure((size_t)(B + 1) * 8, 0, s->stream));
-    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + B;
-    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(B + 1) * 8, s->stream));
+    B2_TRY(s->ws.thr.ensure((size_t)(2 * B + 1) * 8, 0, s->stream));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 2 * B;
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(2 * B + 1) * 8, s->stream));
     B2_TRY(s->ws.lists_a.ensure((size_t)B * dense_gemm_nlists(s) * Lc * 8, 0, s->stream));
     int nlists = 0;
     B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, out_scores_dev));

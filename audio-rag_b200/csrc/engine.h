@@ -57,7 +57,7 @@ constexpr int kSparseThreads = 256;
 constexpr int kMaxQueryTermsChunk = 256;
 constexpr int kMergeMaxKeys = 8192;    // smem bound of one merge group
 constexpr int kMergeGroupKeys = 1024;  // preferred group size (keeps the bitonic network short)
-constexpr int kTailMaxKeys = 65536;    // most candidate keys (n_lists * Lc) the fused leg tail takes in one launch
+constexpr int kTailMaxKeys = 1 << 20;  // most candidate keys (n_lists * Lc) the fused leg tail takes in one launch
 
 struct DevPtr {
     void* p = nullptr;
@@ -128,6 +128,7 @@ struct Shard {
     bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
+    int thr_par = 0;                      // which of the two threshold sets in ws.thr the dense scan uses (pipelined mode)
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
     // Pipelined mode (b200rag_set_pipeline): ONLY the dense scan runs on `stream`; the sparse leg, both legs' tails,
@@ -231,8 +232,10 @@ int launch_finalize_leg(Shard* s, int batch, int Lc, int L, const uint64_t* appr
                         b200rag_cand* out, int32_t* ambiguous);
 // merge (all levels) + exact re-score + finalize in one launch, when n_lists * Lc keys fit (leg_tail_fits)
 bool leg_tail_fits(int n_lists, int Lc);
+// gkey: [batch] the scan's final grid-wide threshold keys (0 = none) or nullptr
 int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L, const uint64_t* lists, float eps_abs,
-                    float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous);
+                    float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out, int32_t* ambiguous,
+                    const uint64_t* gkey = nullptr);
 int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, const b200rag_cand* gathered,
                 int n_shards, int has_trailer, int64_t* out_ids, double* out_scores, int32_t* out_counts,
                 int64_t shard_stride_override = 0, const unsigned long long* wait_flags = nullptr,
@@ -251,7 +254,7 @@ int launch_fill_row_ids(Shard* s, int64_t* dst, int64_t first_id, int64_t n);
 // ---- sparse.cu -----------------------------------------------------------------------------------------
 int build_inverted(Shard* s);
 int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, float* q_eps /*[batch]*/,
-                       int* gthr /*[batch], preset to INT_MIN*/);
+                       int* gthr /*[batch], preset to INT_MIN*/, uint64_t* gkey /*[batch], preset to 0, or null*/);
 int sparse_scan_nlists(const Shard* s, int batch, int Lc);
 
 // ---- synth.cu ------------------------------------------------------------------------------------------

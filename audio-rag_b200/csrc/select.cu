@@ -114,10 +114,11 @@ int launch_rescore_dense(Shard* s, int batch, int64_t Lc, const uint64_t* approx
 }
 
 // Exact sparse score of one document against one chunk of query terms (<= kMaxQueryTermsChunk, ascending, in shared
-// memory), by one warp.  The DOCUMENT's terms are streamed with coalesced loads (~200 per 256-token chunk: 6 rounds) and
-// each is looked up in the query chunk by binary search in shared memory -- one global round trip instead of a chain of
-// dependent global loads per query term.  Products land in prod[j] (j = position of the term in the query), lane 0 then
-// adds them in ascending j = ascending term index: the canonical order of SURVEY R3, bit-equal to the oracle.
+// memory), by one warp.  The DOCUMENT's terms and weights are streamed with coalesced loads, 256 per round and all of a
+// round's loads in flight at once (~200 terms per 256-token chunk: one round), and each term is looked up in the query
+// chunk by binary search in shared memory -- one global round trip instead of a chain of dependent loads per query term.
+// Products land in prod[j] (j = position of the term in the query), lane 0 then adds them in ascending j = ascending
+// term index: the canonical order of SURVEY R3, bit-equal to the oracle.
 __device__ __forceinline__ void sparse_exact_chunk(int64_t ds, int64_t de, const uint32_t* __restrict__ fwd_terms,
                                                    const float* __restrict__ fwd_w, const uint32_t* qt, const float* qw,
                                                    int cn, double* prod, uint8_t* present, int lane, double& acc,
@@ -125,17 +126,28 @@ __device__ __forceinline__ void sparse_exact_chunk(int64_t ds, int64_t de, const
     for (int j = lane; j < cn; j += 32) present[j] = 0;
     __syncwarp();
     const uint32_t tlo = qt[0], thi = qt[cn - 1];
-    for (int64_t i = ds + lane; i < de; i += 32) {
-        const uint32_t t = fwd_terms[i];
-        if (t < tlo || t > thi) continue;
-        int lo = 0, hi = cn;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (qt[mid] < t) lo = mid + 1; else hi = mid;
+    for (int64_t i0 = ds; i0 < de; i0 += 256) {      // 256 document terms per round: 8 term + 8 weight loads in flight per lane
+        uint32_t t8[8];
+        float w8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t i = i0 + u * 32 + lane;
+            t8[u] = i < de ? fwd_terms[i] : 0xFFFFFFFFu;
+            w8[u] = i < de ? fwd_w[i] : 0.f;
         }
-        if (lo < cn && qt[lo] == t) {
-            present[lo] = 1;
-            prod[lo] = __dmul_rn((double)qw[lo], (double)fwd_w[i]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t t = t8[u];
+            if (t < tlo || t > thi) continue;
+            int lo = 0, hi = cn;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (qt[mid] < t) lo = mid + 1; else hi = mid;
+            }
+            if (lo < cn && qt[lo] == t) {
+                present[lo] = 1;
+                prod[lo] = __dmul_rn((double)qw[lo], (double)w8[u]);
+            }
         }
     }
     __syncwarp();
@@ -293,6 +305,7 @@ __device__ __forceinline__ uint64_t rescore_dense_warp(const uint16_t* __restric
 
 struct TailParams {
     const uint64_t* lists;   // [batch][n_lists][Lc]
+    const uint64_t* gkey;    // [batch] or null: the scan's grid-wide threshold key (>= Lc listed keys are at or above it)
     int n_lists, Lc, L;
     // dense re-score
     const uint16_t* corpus;
@@ -327,9 +340,14 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
     const uint64_t* src = p.lists + (size_t)q * total;
     if (tid == 0) { cnt_s = 0; nvalid_s = 0; }
 
-    // ---- 1. threshold from thread maxima, survivors, sort
+    // ---- 1. threshold, survivors, sort
+    // Threshold from the thread maxima: every thread keeps the maximum of its strided slice, every warp sorts its 32
+    // maxima and publishes its k-th largest, k = ceil(Lc / #warps); the minimum over the warps has >= Lc keys at or above
+    // it.  The scans' own grid-wide threshold (p.gkey: the Lc-th best key of SOME list) is a second valid bound -- a much
+    // weaker one (at 10M rows it let 12 000 of 31 700 keys through where the maxima let ~100 through), but the only one
+    // when Lc exceeds 32 keys per warp -- so the tighter of the two is used.
     uint64_t tmax = 0;
-    for (int i = tid; i < total; i += NT) {
+    for (int i = tid; i < total; i += NT) {            // (independent loads: the compiler batches them)
         const uint64_t k = src[i];
         tmax = k > tmax ? k : tmax;
     }
@@ -351,38 +369,71 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
     uint64_t tau = wk_s[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) tau = wk_s[w] < tau ? wk_s[w] : tau;
+    {
+        const uint64_t gk = p.gkey != nullptr ? p.gkey[q] : 0ull;
+        tau = gk > tau ? gk : tau;
+    }
     if (tau == 0) tau = 1;                 // fewer than Lc real keys: keep every non-empty slot
-    for (int i0 = warp * 32; i0 < total; i0 += NT) {      // warp-uniform trip count: one shared atomic per warp and round
-        const int i = i0 + lane;
-        const uint64_t k = i < total ? src[i] : 0ull;
-        const bool take = k >= tau;
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (m != 0) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&cnt_s, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            if (take && pos < kTailSurvivorCap) tkeys[pos] = k;
+    // survivors: four keys per thread and round in flight, one shared atomic per warp and key group (warp-uniform trips)
+    for (int i0 = warp * 128; i0 < total; i0 += NT * 4) {
+        uint64_t k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            k4[u] = i < total ? src[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool take = k4[u] >= tau;
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (m != 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&cnt_s, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (take && pos < kTailSurvivorCap) tkeys[pos] = k4[u];
+            }
         }
     }
     __syncthreads();
     int M = cnt_s;
     if (M > kTailSurvivorCap) {
-        // (massive ties) exact Lc-th largest key by bisection on the key bits, then exactly the keys >= it
-        __shared__ int c_s;
-        uint64_t K = 0;
-        for (int bit = 63; bit >= 0; --bit) {
-            const uint64_t cand = K | (1ull << bit);
-            int c = 0;
-            for (int i = tid; i < total; i += NT) c += src[i] >= cand ? 1 : 0;
-            if (tid == 0) c_s = 0;
+        // Too many survivors (massive ties, or no usable threshold over very many lists): radix-select the exact Lc-th
+        // largest KEY -- six histogram passes over the 64 key bits (11 + 11 + 10 score bits, 11 + 11 + 10 row bits)
+        // instead of one counting pass per bit -- then keep exactly the keys at or above it (keys are unique).
+        int* hist = reinterpret_cast<int*>(tkeys);         // 2048 bins; the overflowed survivor area is free
+        __shared__ int need_s;
+        __shared__ unsigned long long pref_s;
+        unsigned long long prefix = 0;
+        int need = p.Lc, hi = 64;
+        __syncthreads();
+#pragma unroll 1
+        for (int d = 0; d < 6; ++d) {
+            const int w = (d % 3 == 2) ? 10 : 11;
+            const int shift = hi - w;
+            for (int i = tid; i < (1 << w); i += NT) hist[i] = 0;
             __syncthreads();
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0 && c) atomicAdd(&c_s, c);
+            for (int i = tid; i < total; i += NT) {
+                const unsigned long long k = src[i];
+                if (k != 0 && (hi == 64 || (k >> hi) == prefix)) atomicAdd(&hist[(int)((k >> shift) & ((1ull << w) - 1ull))], 1);
+            }
             __syncthreads();
-            if (c_s >= p.Lc) K = cand;
+            if (tid == 0) {
+                int acc = 0, b = (1 << w) - 1;
+                for (; b > 0; --b) {
+                    if (acc + hist[b] >= need) break;
+                    acc += hist[b];
+                }
+                need_s = need - acc;
+                pref_s = (prefix << w) | (unsigned long long)b;
+            }
+            __syncthreads();
+            need = need_s;
+            prefix = pref_s;
+            hi = shift;
             __syncthreads();
         }
+        const uint64_t K = prefix;
         if (tid == 0) cnt_s = 0;
         __syncthreads();
         for (int i = tid; i < total; i += NT) {
@@ -411,10 +462,14 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
             if (lane == 0) tkeys[i] = ex;
         }
     } else {
-        __shared__ uint32_t qt[kMaxQueryTermsChunk];
-        __shared__ float qw[kMaxQueryTermsChunk];
-        __shared__ double prod[NW][kMaxQueryTermsChunk];
-        __shared__ uint8_t present[NW][kMaxQueryTermsChunk];
+        // dynamic shared memory behind the survivor area:
+        //   prod [NW][chunk] f64 | qt [chunk] u32 | qw [chunk] f32 | present [NW][chunk] u8
+        double* prod_base = reinterpret_cast<double*>(tkeys + kTailSurvivorCap);
+        uint32_t* qt = reinterpret_cast<uint32_t*>(prod_base + (size_t)NW * kMaxQueryTermsChunk);
+        float* qw = reinterpret_cast<float*>(qt + kMaxQueryTermsChunk);
+        uint8_t* present_base = reinterpret_cast<uint8_t*>(qw + kMaxQueryTermsChunk);
+        double* prod_w = prod_base + (size_t)warp * kMaxQueryTermsChunk;
+        uint8_t* present_w = present_base + (size_t)warp * kMaxQueryTermsChunk;
         const int64_t qs = p.q_indptr[q], qe = p.q_indptr[q + 1];
         for (int i0 = 0; i0 < p.Lc; i0 += NW) {
             const int i = i0 + warp;
@@ -431,7 +486,7 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
                 __syncthreads();
                 if (active) {
                     int touched = 0;
-                    sparse_exact_chunk(ds, de, p.fwd_terms, p.fwd_w, qt, qw, cn, prod[warp], present[warp], lane, acc, touched);
+                    sparse_exact_chunk(ds, de, p.fwd_terms, p.fwd_w, qt, qw, cn, prod_w, present_w, lane, acc, touched);
                 }
             }
             if (i < p.Lc && lane == 0) tkeys[i] = active ? make_key(__double2float_rn(acc) + 0.0f, row) : 0ull;
@@ -483,26 +538,32 @@ bool leg_tail_fits(int n_lists, int Lc) { return (int64_t)n_lists * Lc <= kTailM
 
 int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L, const uint64_t* lists, float eps_abs,
                     float eps_rel, const float* eps_abs_q, int has_thr, float thr, b200rag_cand* out,
-                    int32_t* ambiguous) {
+                    int32_t* ambiguous, const uint64_t* gkey) {
     TailParams p{};
-    p.lists = lists; p.n_lists = n_lists; p.Lc = Lc; p.L = L;
+    p.lists = lists; p.gkey = gkey; p.n_lists = n_lists; p.Lc = Lc; p.L = L;
     p.corpus = s->dense.as<uint16_t>(); p.dim = s->dim; p.q_bits = s->ws.q_bits.as<uint16_t>();
     p.fwd_ptr = s->fwd_ptr.as<int64_t>(); p.fwd_terms = s->fwd_terms.as<uint32_t>(); p.fwd_w = s->fwd_w.as<float>();
     p.q_indptr = s->ws.q_sp_indptr.as<int64_t>(); p.q_terms = s->ws.q_sp_terms.as<uint32_t>(); p.q_w = s->ws.q_sp_w.as<float>();
     p.eps_abs = eps_abs; p.eps_rel = eps_rel; p.eps_abs_q = eps_abs_q; p.has_thr = has_thr; p.thr = thr;
     p.row_ids = s->row_ids.as<int64_t>(); p.out = out; p.ambiguous = ambiguous;
     const size_t smem = (size_t)kTailSurvivorCap * 8;
+    auto sparse_smem = [&](int nw) { return smem + (size_t)nw * kMaxQueryTermsChunk * 9 + (size_t)kMaxQueryTermsChunk * 8; };
     static AttrCache attr;
-    if (attr.raise(s->cfg.device, smem)) {     // static + dynamic shared memory exceeds the 48 KB default of the sparse flavour
-        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (attr.raise(s->cfg.device, sparse_smem(32))) {
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sparse_smem(8)));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sparse_smem(32)));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // the sparse leg's tail runs beside the dense scan: same carve-out, or it would wait for the scan's SMs to drain
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 1024>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    if (sparse) leg_tail_kernel<true, 256><<<batch, 256, smem, s->stream>>>(p);
+    // more than 64 candidates per leg (top-k beyond ~20): 32 warps, so that the per-warp k-th-largest threshold works
+    // (k = ceil(Lc / #warps) <= 32) and 32 candidates are re-scored at a time
+    if (sparse && Lc > 64) leg_tail_kernel<true, 1024><<<batch, 1024, sparse_smem(32), s->stream>>>(p);
+    else if (sparse) leg_tail_kernel<true, 256><<<batch, 256, sparse_smem(8), s->stream>>>(p);
     else if (Lc > 64) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);   // 32 warps re-score in parallel
     else leg_tail_kernel<false, 512><<<batch, 512, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());

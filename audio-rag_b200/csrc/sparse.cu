@@ -48,6 +48,7 @@ struct SparseScanParams {
     int Lc, n_blocks, sel_cap;
     int bpc, n_groups;             // blocks per CTA, CTAs per query
     int* gthr;                     // [batch] grid-wide pruning thresholds in fixed-point units (INT_MIN = none yet)
+    unsigned long long* gkey;      // [batch] the same as a candidate KEY (0 = none yet): the leg tail's survivor threshold
     float w_absmax;                // max |w_d| over the shard's postings: bounds every score by sum|w_q| * w_absmax
     float* q_eps;                  // [batch] out: absolute error bound of this query's approximate scores
     unsigned long long* post_count;
@@ -199,7 +200,11 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) sparse_scan_kernel(cons
         if (M >= p.Lc) {
             const int t = __float2int_rn(key_score(sel[p.Lc - 1]) * S);   // exact: |v| < 2^23 and S is a power of two
             if (t > tau) tau = t;
-            if (tid == 0) { cnt_s = p.Lc; if (p.gthr != nullptr) atomicMax(&p.gthr[q], tau); }
+            if (tid == 0) {
+                cnt_s = p.Lc;
+                if (p.gthr != nullptr) atomicMax(&p.gthr[q], tau);
+                if (p.gkey != nullptr) atomicMax(&p.gkey[q], (unsigned long long)sel[p.Lc - 1]);   // Lc listed keys are >= it
+            }
         }
         __syncthreads();
     };
@@ -435,21 +440,12 @@ static int launch_scan_nt(Shard* s, const SparseScanParams& p, int batch) {
 }
 
 // blocks per CTA: as many as possible (the running threshold prunes better) while the grid still has ~4 waves of CTAs
-// ... and, for large top-k, enough blocks per CTA that the leg's n_lists * Lc candidate keys still fit the fused tail
-// (one launch instead of merge tree + re-score + finalize: at 12.5M rows, top-100, 1 526 lists x 300 keys took the slow
-// path and the leg's tail cost 0.36 ms; 7 blocks per CTA give 218 lists, and the longer scan hides behind the dense one)
 int sparse_scan_bpc(const Shard* s, int batch, int Lc) {
+    (void)Lc;      // (the fused leg tail takes up to 2^20 keys: 12.5M rows x top-100 = 1 526 lists x 300 keys fit as they are)
     if (s->sparse_bpc > 0) return s->sparse_bpc;
     const int64_t items = (int64_t)s->n_blocks * batch;
     int64_t bpc = items / ((int64_t)4 * s->sm_count * 8);
     if (bpc < 1) bpc = 1;
-    if (Lc > 0 && s->fused_tail) {
-        const int64_t max_lists = kTailMaxKeys / Lc;
-        if (max_lists >= 1) {
-            const int64_t need = (s->n_blocks + max_lists - 1) / max_lists;
-            if (need > bpc && need <= 32) bpc = need;
-        }
-    }
     if (bpc > 32) bpc = 32;
     return (int)bpc;
 }
@@ -458,7 +454,7 @@ int sparse_scan_nlists(const Shard* s, int batch, int Lc) {
     return (int)((s->n_blocks + bpc - 1) / bpc);
 }
 
-int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, float* q_eps, int* gthr) {
+int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, float* q_eps, int* gthr, uint64_t* gkey) {
     SparseScanParams p{};
     p.dir = s->dir.as<uint32_t>();
     p.blk_base = s->blk_base.as<int64_t>();
@@ -480,6 +476,7 @@ int launch_sparse_scan(Shard* s, int batch, int Lc, uint64_t* out_lists, float* 
     p.w_absmax = s->w_absmax;
     p.q_eps = q_eps;
     p.gthr = gthr;
+    p.gkey = reinterpret_cast<unsigned long long*>(gkey);
     p.post_count = s->ws.post_count.as<unsigned long long>();
     if (Lc > kSelCapMax) { set_error("sparse_scan: top-k too large"); return B200RAG_ERR_INVALID; }
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[2], s->stream)); }

@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000)
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the full-corpus oracle check (profiling runs)")
     return ap.parse_args()
 
 
@@ -509,7 +510,8 @@ def run_b200(a):
 
     # ------------------------------------------------------------------ (4) oracle check, outside every timed region
     try:
-        ocheck = oracle_check(a, sh, kept, step_arrays, world, rank, dev)
+        ocheck = {"queries": 0, "mismatches": None, "skipped": "--no-oracle-check"} if a.no_oracle_check else \
+            oracle_check(a, sh, kept, step_arrays, world, rank, dev)
     except Exception as e:
         ocheck = {"queries": 0, "mismatches": None, "error": repr(e)}
 

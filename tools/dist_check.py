@@ -18,18 +18,11 @@ from helpers import Corpus, oracle_search  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    # B200RAG_SAME_DEVICE=1: every rank uses GPU 0 and the control plane is gloo (NCCL refuses two ranks on one GPU).  The
-    # candidate exchange is the same code -- CUDA-IPC windows, peer stores, epoch flags at system scope -- between
-    # PROCESSES that time-slice one GPU: a functional check of the multi-rank protocol on a 1-GPU box.
-    same = os.environ.get("B200RAG_SAME_DEVICE", "0") == "1"
-    if same:
-        local = 0
+    # (one rank per GPU only: ranks whose fuse kernels wait on each other's flags must never share a GPU -- nothing
+    #  guarantees that time-sliced processes run at the same time, see B200_PROFILING.md)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if same:
-        dist.init_process_group("gloo")
-    else:
-        dist.init_process_group("nccl", device_id=dev)
+    dist.init_process_group("nccl", device_id=dev)
     n, dim = 40_000, 1024
     c = Corpus(n, dim=dim, vocab=60_013)
     lo, hi = shard_bounds(n, world, rank, align=16)
@@ -82,8 +75,7 @@ def main():
     tot = torch.tensor([bad], device=dev)
     dist.all_reduce(tot)
     if rank == 0:
-        print(f"dist_check world={world} p2p={ss.p2p} pipelined_tail={ss.pipeline}"
-              f"{' same_device(gloo control plane)' if same else ''}: mismatches={int(tot.item())}", flush=True)
+        print(f"dist_check world={world} p2p={ss.p2p} pipelined_tail={ss.pipeline}: mismatches={int(tot.item())}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(1 if int(tot.item()) else 0)
