@@ -214,10 +214,10 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     int Lc = L + slack;
     if (Lc > 3 * B200RAG_MAX_TOPK) Lc = 3 * B200RAG_MAX_TOPK;
 
-    // thr: [2][B] grid-wide dense thresholds (one set per call parity: in pipelined mode the previous search's tail
-    // still reads its set while this search's scan raises the other) | [1] postings counter
-    B2_TRY(s->ws.thr.ensure((size_t)(2 * B + 1) * 8, 0, st));
-    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 2 * B;
+    // thr: per call parity [B grid-wide dense thresholds | B dense-scan tile counters] (two sets: in pipelined mode the
+    // previous search's tail still reads its thresholds while this search's scan raises the other set) | postings counter
+    B2_TRY(s->ws.thr.ensure((size_t)(4 * B + 1) * 8, 0, st));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 4 * B;
     B2_TRY(s->ws.exact.ensure((size_t)B * Lc * 8, 0, st));
 
     const bool want_dense = q.mode != B200RAG_SPARSE;
@@ -252,8 +252,12 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
 
     // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
     const int nl_scan = dense_scan_nlists(s);
+    // (only while the tails are light, i.e. up to 64 candidates per leg: the tails of search i run beside the dense scan
+    //  of search i+1, whose tiles are split statically over the SMs, so a heavy tail -- top-100: 300 candidates to
+    //  re-score -- holds back the SM it shares and with it the whole scan: 12.5M rows, top-100: 4.37 ms per step pipelined,
+    //  4.19 ms in the classic form.  Claiming tiles dynamically instead costs more than it saves: B200RAG_SCAN_DYNAMIC.)
     const bool piped = s->pipeline && !s->pipeline_paused && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
-                       leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
+                       Lc <= 64 && leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
     if (piped) {
         cudaStream_t sd = s->pipe_stream;
         const int par = (int)(s->legs_calls & 1);                 // (legs_calls was incremented by the caller)
@@ -265,7 +269,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         if (want_dense) {
             B2_TRY(lists.ensure((size_t)B * nl_scan * Lc * 8, 0, st));
             if (s->ev_tail_rec[par]) B2_CUDA(cudaStreamWaitEvent(st, s->ev_tail[par], 0));
-            B2_CUDA(cudaMemsetAsync(s->ws.thr.as<uint64_t>() + (size_t)par * B, 0, (size_t)B * 8, st));
+            B2_CUDA(cudaMemsetAsync(s->ws.thr.as<uint64_t>() + (size_t)par * 2 * B, 0, (size_t)2 * B * 8, st));
         }
         B2_CUDA(cudaEventRecord(s->ev_fork, st));                  // side-stream work of this search starts after this point
         B2_CUDA(cudaStreamWaitEvent(sd, s->ev_fork, 0));
@@ -307,7 +311,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
             if (rc == B200RAG_OK) rc = launch_leg_tail(s, false, B, nlists, Lc, L, lists.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
                                                        q.score_threshold, out_dense, ambiguous,
-                                                       s->ws.thr.as<uint64_t>() + (size_t)par * B);
+                                                       s->ws.thr.as<uint64_t>() + (size_t)par * 2 * B);
             if (rc == B200RAG_OK) {
                 e = cudaEventRecord(s->ev_tail[par], sd);
                 if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord(tail)"); else s->ev_tail_rec[par] = true;
@@ -317,7 +321,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         return rc;
     }
     if (s->pipeline) B2_TRY(pipeline_drain(s));     // classic form below: the side stream's earlier searches must be through
-    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(2 * B + 1) * 8, st));
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(4 * B + 1) * 8, st));
 
     // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
     // nothing could co-reside.  The FILTER epilogue keeps no per-query state (96 registers); with one pipeline stage
@@ -550,6 +554,8 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_OVERLAP_GEMM")) s->overlap_gemm = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
+    if (const char* e = getenv("B200RAG_SCAN_DYNAMIC")) s->scan_dynamic = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_SCAN_CTAS")) s->scan_ctas = atoi(e);
     if (const char* e = getenv("B200RAG_EXACT_FALLBACK")) s->exact_fallback = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_P2P_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms > 0) s->x_timeout_cycles = ms * 2000000ll; }
     if (const char* e = getenv("B200RAG_BULK_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) s->bulk_split = v; }
@@ -678,9 +684,9 @@ int b200rag_debug_dense_scores(b200rag_shard* sp, float* out_scores_dev) {
     if (s->n_rows == 0) return B200RAG_OK;
     B2_TRY(use_device(s));
     const int B = s->q.batch, Lc = 16;
-    B2_TRY(s->ws.thr.ensure((size_t)(2 * B + 1) * 8, 0, s->stream));
-    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 2 * B;
-    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(2 * B + 1) * 8, s->stream));
+    B2_TRY(s->ws.thr.ensure((size_t)(4 * B + 1) * 8, 0, s->stream));
+    s->ws.post_count.p = s->ws.thr.as<uint64_t>() + 4 * B;
+    B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(4 * B + 1) * 8, s->stream));
     B2_TRY(s->ws.lists_a.ensure((size_t)B * dense_gemm_nlists(s) * Lc * 8, 0, s->stream));
     int nlists = 0;
     B2_TRY(launch_dense_gemm(s, B, Lc, s->ws.lists_a.as<uint64_t>(), &nlists, out_scores_dev));

@@ -129,6 +129,9 @@ struct Shard {
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
     int thr_par = 0;                      // which of the two threshold sets in ws.thr the dense scan uses (pipelined mode)
+    bool scan_dynamic = false;            // knob (B200RAG_SCAN_DYNAMIC): dense-scan tiles claimed from a grid-wide counter
+                                          // (measured: 28 % SLOWER at 10M rows -- 148 producers on one L2 atomic -- off)
+    int scan_ctas = 0;                    // knob (B200RAG_SCAN_CTAS): dense-scan grid size (0 = one CTA per SM)
     int slack = 0;
     int dense_path = 0;  // 0 = auto (SIMT scan for <= 2 queries, tcgen05 GEMM above), 1 = SIMT, 2 = tcgen05
     // Pipelined mode (b200rag_set_pipeline): ONLY the dense scan runs on `stream`; the sparse leg, both legs' tails,

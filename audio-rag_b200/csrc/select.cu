@@ -552,6 +552,8 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
     if (attr.raise(s->cfg.device, sparse_smem(32))) {
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sparse_smem(8)));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sparse_smem(32)));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sparse_smem(16)));
+        B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<true, 512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // the sparse leg's tail runs beside the dense scan: same carve-out, or it would wait for the scan's SMs to drain
@@ -560,11 +562,16 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         B2_CUDA(cudaFuncSetAttribute(leg_tail_kernel<false, 1024>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    // more than 64 candidates per leg (top-k beyond ~20): 32 warps, so that the per-warp k-th-largest threshold works
-    // (k = ceil(Lc / #warps) <= 32) and 32 candidates are re-scored at a time
-    if (sparse && Lc > 64) leg_tail_kernel<true, 1024><<<batch, 1024, sparse_smem(32), s->stream>>>(p);
+    // More than 64 candidates per leg (top-k beyond ~20): more warps, so that the per-warp k-th-largest threshold works
+    // (k = ceil(Lc / #warps) <= 32) and more candidates are re-scored at a time -- 32 warps when the tail runs alone,
+    // 16 in pipelined mode, where it must CO-RESIDE with the next search's dense scan (a 1024-thread CTA does not fit the
+    // register file beside a scan CTA: it would wait for the whole scan to drain and serialise the pipeline; measured at
+    // 12.5M rows, top-100: 4.9 ms per step instead of 4.1).
+    const bool beside_scan = s->pipeline && !s->pipeline_paused;
+    if (sparse && Lc > 64 && !beside_scan) leg_tail_kernel<true, 1024><<<batch, 1024, sparse_smem(32), s->stream>>>(p);
+    else if (sparse && Lc > 64) leg_tail_kernel<true, 512><<<batch, 512, sparse_smem(16), s->stream>>>(p);
     else if (sparse) leg_tail_kernel<true, 256><<<batch, 256, sparse_smem(8), s->stream>>>(p);
-    else if (Lc > 64) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);   // 32 warps re-score in parallel
+    else if (Lc > 64 && !beside_scan) leg_tail_kernel<false, 1024><<<batch, 1024, smem, s->stream>>>(p);
     else leg_tail_kernel<false, 512><<<batch, 512, smem, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
@@ -809,7 +816,9 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
-    const int fuse_threads = (size_t)n_shards * L > 512 ? 1024 : 256;     // the bitonic merge of large sets wants more lanes
+    // the bitonic merge of large sets wants more lanes; in pipelined mode the kernel must fit beside a dense-scan CTA
+    const bool beside_scan = s->pipeline && !s->pipeline_paused;
+    const int fuse_threads = (size_t)n_shards * L > 512 ? (beside_scan ? 512 : 1024) : 256;
     fuse_kernel<<<batch, fuse_threads, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
                                                  rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch,
                                                  s->x_timeout_cycles);
