@@ -61,7 +61,7 @@ def launches(cap, name, steps):
     for k, v in timed:
         per[k] = per.get(k, 0.0) + v / steps
     tot = sum(per.values())
-    json.dump({"cmd": "python bench.py --steps 3 --warmup 3 --no-cpu-baseline", "steps_summarised": steps,
+    json.dump({"cmd": "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-oracle-check", "steps_summarised": steps,
                "us_per_step": {k: round(v, 2) for k, v in per.items()},
                "share": {k: round(v / tot, 4) for k, v in per.items()},
                "total_us_per_step_serialised": round(tot, 1)},
