@@ -198,6 +198,10 @@ static int pipeline_drain(Shard* s) {
     return B200RAG_OK;
 }
 // ... and afterwards the side stream (where exchange and fuse are enqueued) waits for the legs the main stream ran
+// exchange + fuse of a search run where its tails ran: on the second stream after pipelined legs, on `stream` otherwise
+static bool tail_on_second_stream(const Shard* s) {
+    return s->x_stream != nullptr && !s->pipeline_paused && !s->legs_classic;
+}
 static int pipeline_handover(Shard* s) {
     B2_CUDA(cudaEventRecord(s->ev_fork, s->stream));
     B2_CUDA(cudaStreamWaitEvent(s->pipe_stream, s->ev_fork, 0));
@@ -225,6 +229,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     if (s->exhaustive) {
         // always-exact path: canonical score of every eligible row + full sort, no scan kernels, never ambiguous
         if (s->pipeline) B2_TRY(pipeline_drain(s));
+        if (ambiguous != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous, 0, 4, st));
         s->stats.exhaustive = 1;
         b200rag_cand* o = cands;
         if (want_dense) {
@@ -236,7 +241,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             if (s->n_rows == 0 || s->nnz == 0 || s->staged_q_terms == 0) B2_CUDA(cudaMemsetAsync(o, 0, (size_t)B * L * sizeof(b200rag_cand), st));
             else B2_TRY(launch_exhaustive_leg(s, true, B, L, 0, 0.f, o));
         }
-        if (s->pipeline && !s->pipeline_paused) B2_TRY(pipeline_handover(s));
+        s->legs_classic = s->pipeline && !s->pipeline_paused;
         return B200RAG_OK;
     }
     if (want_sparse && s->built_rows != s->n_rows) {
@@ -318,9 +323,11 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             }
         }
         s->stream = st;
+        s->legs_classic = false;
         return rc;
     }
     if (s->pipeline) B2_TRY(pipeline_drain(s));     // classic form below: the side stream's earlier searches must be through
+    if (ambiguous != nullptr) B2_CUDA(cudaMemsetAsync(ambiguous, 0, 4, st));   // callers need not pre-zero the counter
     B2_CUDA(cudaMemsetAsync(s->ws.thr.p, 0, (size_t)(4 * B + 1) * 8, st));
 
     // Batched hybrid (tcgen05 path): the list epilogues need most of the register file and all of shared memory, so
@@ -413,7 +420,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         B2_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
         B2_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     }
-    if (s->pipeline && !s->pipeline_paused) B2_TRY(pipeline_handover(s));
+    s->legs_classic = s->pipeline && !s->pipeline_paused;      // exchange + fuse follow on this stream, then the hand-over
     (void)nlegs;
     return B200RAG_OK;
 }
@@ -1068,10 +1075,7 @@ int b200rag_legs(b200rag_shard* sp, void* cands_dev, int32_t* ambiguous_dev) {
     s->ev_dense = s->ev_sparse = s->ev_in = s->ev_out = false;
     if (s->profile) { B2_CUDA(cudaEventRecord(s->ev[4], s->stream)); s->ev_in = true; }
     // callers need not pre-zero the counter (pipelined mode: the legs zero it on the stream their tails run on)
-    if (ambiguous_dev != nullptr && (!s->pipeline || s->pipeline_paused)) {
-        if (s->pipeline) B2_TRY(pipeline_drain(s));        // (paused: earlier pipelined searches may still use the counter)
-        B2_CUDA(cudaMemsetAsync(ambiguous_dev, 0, 4, s->stream));
-    }
+    // (the legs zero the ambiguity counter themselves, on the stream their tails run on: run_legs)
     return run_legs(s, (b200rag_cand*)cands_dev, ambiguous_dev);
 }
 
@@ -1086,13 +1090,14 @@ int b200rag_fuse(b200rag_shard* sp, const void* gathered, int32_t n_shards, int3
     B2_TRY(use_device(s));
     const int L = s->q.mode == B200RAG_HYBRID ? 2 * s->q.top_k : s->q.top_k;
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;       // pipelined mode: the fuse follows the tails
+    if (tail_on_second_stream(s)) s->stream = s->x_stream;       // pipelined mode: the fuse follows the tails
     int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, (const b200rag_cand*)gathered, n_shards,
                          has_trailer, out_ids, out_scores, out_counts);
     if (rc == B200RAG_OK && s->profile) {
         if (cudaEventRecord(s->ev[5], s->stream) == cudaSuccess) s->ev_out = true; else rc = cuda_fail(cudaGetLastError(), "cudaEventRecord");
     }
     s->stream = keep;
+    if (rc == B200RAG_OK && s->legs_classic) rc = pipeline_handover(s);   // results are read on the second stream
     return rc;
 }
 
@@ -1387,7 +1392,7 @@ int b200rag_p2p_exchange(b200rag_shard* sp, const void* mine, int64_t nbytes) {
     B2_TRY(use_device(s));
     ++s->x_epoch;
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;
+    if (tail_on_second_stream(s)) s->stream = s->x_stream;
     const int rc = launch_exchange(s, mine, nbytes, s->ws.xpeers_dev.as<void*>(), s->x_world, s->x_rank, s->x_slot_bytes,
                                    (int)(s->x_epoch & 1ull), s->x_epoch);
     s->stream = keep;
@@ -1414,13 +1419,14 @@ int b200rag_p2p_fuse(b200rag_shard* sp, int64_t* out_ids, double* out_scores, in
     const b200rag_cand* gathered = (const b200rag_cand*)(win + (size_t)(s->x_epoch & 1ull) * s->x_world * s->x_slot_bytes);
     const unsigned long long* flags = (const unsigned long long*)(win + (size_t)2 * s->x_world * s->x_slot_bytes);
     cudaStream_t keep = s->stream;
-    if (s->x_stream != nullptr && !s->pipeline_paused) s->stream = s->x_stream;
+    if (tail_on_second_stream(s)) s->stream = s->x_stream;
     int rc = launch_fuse(s, s->q.mode, s->q.batch, L, s->q.top_k, s->q.rrf_k, gathered, s->x_world, 1, out_ids, out_scores,
                          out_counts, s->x_slot_bytes / (int64_t)sizeof(b200rag_cand), flags, s->x_epoch);
     if (rc == B200RAG_OK && s->profile) {
         if (cudaEventRecord(s->ev[5], s->stream) == cudaSuccess) s->ev_out = true; else rc = cuda_fail(cudaGetLastError(), "cudaEventRecord");
     }
     s->stream = keep;
+    if (rc == B200RAG_OK && s->legs_classic) rc = pipeline_handover(s);   // results are read on the second stream
     return rc;
 }
 

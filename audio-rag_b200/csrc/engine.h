@@ -139,6 +139,9 @@ struct Shard {
     // lists are double-buffered per call parity and ordered with ev_scan / ev_tail.
     int pipeline = 0;
     bool pipeline_paused = false;         // pipelined mode stays set up, but searches take the classic form on `stream`
+    bool legs_classic = false;            // pipelined mode: the last legs took the classic form (heavy tails, tcgen05 batches,
+                                          // exhaustive legs): its exchange + fuse stay on `stream`, the hand-over to the
+                                          // second stream follows the fuse
     cudaStream_t pipe_stream = nullptr;   // the second stream of pipelined mode: the caller's, or side_stream
     cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
     bool ev_tail_rec[2] = {false, false};
