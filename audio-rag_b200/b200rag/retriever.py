@@ -25,6 +25,7 @@ Additive API (no reference counterpart): ``search_batch``, ``search_batch_arrays
 """
 from __future__ import annotations
 
+import array
 import json
 import os
 from collections import OrderedDict
@@ -497,7 +498,15 @@ class B200Retriever(BaseRetriever):
         return out
 
     def _query_arrays(self, embeddings, mode):
-        dense = np.asarray([e.dense for e in embeddings], dtype=np.float32)
+        if len(embeddings) == 1 and isinstance(embeddings[0].dense, list):
+            # the single-query call of the reference (a Python list of floats): array('f') converts it twice as fast as
+            # numpy does (16 vs 32 us for 1024 floats) with the same double -> float rounding
+            try:
+                dense = np.frombuffer(array.array("f", embeddings[0].dense), dtype=np.float32).reshape(1, -1)
+            except (TypeError, OverflowError):
+                dense = np.asarray([embeddings[0].dense], dtype=np.float32)
+        else:
+            dense = np.asarray([e.dense for e in embeddings], dtype=np.float32)
         if dense.ndim != 2 or dense.shape[1] != self.embedding_dim:
             raise RetrievalError(f"query vectors must have dimension {self.embedding_dim}")
         q_bits = _ffi.normalize_bf16(dense)

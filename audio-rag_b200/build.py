@@ -13,7 +13,7 @@ OBJ = os.path.join(HERE, "build")
 SOURCES = ["engine.cu", "dense_scan.cu", "dense_umma.cu", "select.cu", "sparse.cu", "synth.cu", "exact.cu", "group.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--cudart", "shared", "-ccbin", "g++"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "--cudart", "shared", "-ccbin", "g++"]
 
 
 def _newer(src: str, dst: str) -> bool:
@@ -48,7 +48,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(lambda n: _compile(n, verbose), SOURCES))
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-        cmd = [NVCC, "-shared", "--cudart", "shared", "-ccbin", "g++", "-o", OUT, *objs,
+        cmd = [NVCC, "-shared", "--cudart", "shared", "-ccbin", "g++", "-o", OUT, *objs, "-lgomp",
                "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:

@@ -492,22 +492,20 @@ static bool normalize_rows(const float* x, int64_t r0, int64_t r1, int32_t dim, 
 
 int b200rag_normalize_bf16(const float* x, int64_t n, int32_t dim, uint16_t* out) {
     if (x == nullptr || out == nullptr || n < 0 || dim <= 0) { set_error("normalize: bad argument"); return B200RAG_ERR_INVALID; }
-    // rows are independent: batches are split over a few host threads (a 256-query batch costs ~0.8 ms single-threaded,
-    // a sixth of the search it precedes)
-    unsigned hw = std::thread::hardware_concurrency();
-    int nthreads = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 16u), n / 32);
+    // rows are independent: batches are split over the OpenMP team (a pooled team: spawning std::threads per call cost
+    // ~0.5 ms for a 256-query batch, a tenth of the search it precedes; single-threaded the batch takes ~0.8 ms)
+    int nthreads = (int)std::min<int64_t>(16, n / 16);
     bool ok = true;
     if (nthreads <= 1) {
         ok = normalize_rows(x, 0, n, dim, out);
     } else {
-        std::vector<std::thread> pool;
-        std::vector<char> good((size_t)nthreads, 1);
+        int good = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(&& : good)
         for (int t = 0; t < nthreads; ++t) {
             const int64_t r0 = n * t / nthreads, r1 = n * (t + 1) / nthreads;
-            pool.emplace_back([=, &good]() { good[(size_t)t] = normalize_rows(x, r0, r1, dim, out) ? 1 : 0; });
+            good = good && (normalize_rows(x, r0, r1, dim, out) ? 1 : 0);
         }
-        for (auto& th : pool) th.join();
-        for (char g : good) ok = ok && g;
+        ok = good != 0;
     }
     if (!ok) { set_error("normalize: non-finite input"); return B200RAG_ERR_INVALID; }
     return B200RAG_OK;
