@@ -153,6 +153,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of a fully active warp (elect.sync): the warp runs the loop, the elected lane issues the TMA / MMA instructions.
+// With the loop warp-uniform the compiler keeps descriptors, barrier addresses and coordinates in UNIFORM registers; inside
+// an `if (lane == 0)` region it wrapped every UTCHMMA in an ELECT + 5 x R2UR.BROADCAST "waterfall" loop (~15 dependent
+// instructions per MMA: the issue loop then took about as long per k-block as the tensor pipe needs for its 4 MMAs).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // Candidate lists in shared memory, one per query: an UNSORTED set of the Lc best keys seen so far plus, in the
 // owning lane's registers, the fill count and the position/value of the current minimum (= the running threshold).
@@ -248,13 +257,15 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int64_t t = t0; t < t1; ++t) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&empty[st], ph ^ 1u);
-                    uint8_t* sa = gsm + (size_t)st * STAGE_BYTES;
+        // (the whole warp runs the loop, one elected lane issues: see elect_one)
+        const bool elected = elect_one();
+        int st = 0;
+        uint32_t ph = 0;
+        for (int64_t t = t0; t < t1; ++t) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&empty[st], ph ^ 1u);
+                uint8_t* sa = gsm + (size_t)st * STAGE_BYTES;
+                if (elected) {
                     if (CG == 2) {
                         // both CTAs' copies complete on the LEADER's full barrier (which expects the pair's bytes)
                         if (leader) mbar_arrive_expect_tx(&full[st], 2 * STAGE_BYTES);
@@ -266,13 +277,15 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         tma_load_2d(sa, &map_q, &full[st], kb * kGemmKB, 0);
                         tma_load_2d(sa + kStageABytes, &map_c, &full[st], kb * kGemmKB, (int)(t * p.tile_stride * kGemmN));
                     }
-                    if (++st == S) { st = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && leader) {
+        if (leader) {
+            const bool elected = elect_one();
             int st = 0;
             uint32_t ph = 0;
             int it = 0;
@@ -287,16 +300,19 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     const uint32_t sa = smem_u32(gsm + (size_t)st * STAGE_BYTES);
                     const uint64_t da = make_sw128_desc(sa);
                     const uint64_t db = make_sw128_desc(sa + kStageABytes);
+                    if (elected) {
 #pragma unroll
-                    for (int k = 0; k < kGemmKB / 16; ++k) {
-                        if (CG == 2) umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdescPair,
-                                                    (kb | k) != 0 ? 1u : 0u);
-                        else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc,
-                                       (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kGemmKB / 16; ++k) {
+                            if (CG == 2) umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdescPair,
+                                                        (kb | k) != 0 ? 1u : 0u);
+                            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc,
+                                           (kb | k) != 0 ? 1u : 0u);
+                        }
+                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                        if (CG == 2) umma_commit_pair(&empty[st]); else umma_commit(&empty[st]);
+                        if (kb == nkb - 1) { if (CG == 2) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]); }
                     }
-                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-                    if (CG == 2) umma_commit_pair(&empty[st]); else umma_commit(&empty[st]);
-                    if (kb == nkb - 1) { if (CG == 2) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]); }
+                    __syncwarp();
                     if (++st == S) { st = 0; ph ^= 1u; }
                 }
             }
