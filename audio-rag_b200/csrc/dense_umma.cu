@@ -43,7 +43,7 @@ constexpr uint32_t kTmemCols = 512;
 // CTA pair (cta_group::2): M = 256 queries (128 per CTA), N = 256 corpus rows split 128 + 128 between the two CTAs
 constexpr uint32_t kStageBBytesPair = (kGemmN / 2) * kGemmKB * 2;   // 16 KB
 constexpr uint32_t kStageBytesPair = kStageABytes + kStageBBytesPair;
-constexpr int kGemmStagesPair = 6;
+constexpr int kGemmStagesPair = 7;
 
 struct GemmParams {
     const void* corpus;            // for the contiguous L2 prefetch
@@ -161,6 +161,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// v[j] for a run-time j without local memory: a 5-level select tree over the 32 registers (31 selects)
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return __uint_as_float((j & 16) ? d[1] : d[0]) + 0.0f;
+}
 // one lane of a fully active warp (elect.sync): the warp runs the loop, the elected lane issues the TMA / MMA instructions.
 // With the loop warp-uniform the compiler keeps descriptors, barrier addresses and coordinates in UNIFORM registers; inside
 // an `if (lane == 0)` region it wrapped every UTCHMMA in an ELECT + 5 x R2UR.BROADCAST "waterfall" loop (~15 dependent
@@ -237,8 +250,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 2);   // (16 u64 barrier slots precede: 16-byte aligned)
-    float* stage_s = reinterpret_cast<float*>(tmem_base_s + 4);          // [4 epilogue warps][32 lanes][33] score staging
-    uint64_t* lists_s = reinterpret_cast<uint64_t*>(stage_s + 4 * 32 * 33);       // [ceil32(batch)][Lp], 16-byte aligned
+    uint64_t* lists_s = reinterpret_cast<uint64_t*>(tmem_base_s + 4);             // [ceil32(batch)][Lp], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.dim / kGemmKB;
@@ -388,18 +400,16 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if (mask != nullptr) cm &= __ldg(mask + tt * (kGemmN / 32) + c);
                 }
                 if (!__any_sync(0xffffffffu, cm != 0)) continue;
-                // phase B (rare after warm-up): stage the chunk's scores, then insert survivors
-                float* stg = stage_s + (size_t)quad * 32 * 33;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]) + 0.0f;
-                __syncwarp();
+                // phase B (rare after warm-up): insert survivors.  A survivor's score is picked out of the chunk's 32
+                // registers by a select tree (pick32): round 1 staged every chunk's scores in 16.9 KB of shared memory for
+                // this, which is now a 7th pipeline stage for the CTA pairs.
                 // every lane with survivors inserts one of its own per round (up to 32 inserts per round)
                 while (__any_sync(0xffffffffu, cm != 0)) {
                     if (cm != 0) {
                         const int j = __ffs(cm) - 1;
                         cm &= cm - 1;
                         const int64_t row = row0 + j;
-                        const uint64_t key = make_key(stg[lane * 33 + j], (uint32_t)row);
+                        const uint64_t key = make_key(pick32(v, j), (uint32_t)row);
                         const bool ok = LREG < 0 ? key >= thr : key > thr;   // (eligibility was applied to cm already)
                         if constexpr (LREG < 0) {
                             if (ok) {
@@ -426,7 +436,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             }
                         }
                         // survivors flagged against the chunk-start threshold that the new threshold rules out
-                        while (cm != 0 && stg[lane * 33 + (__ffs(cm) - 1)] < thr_s) cm &= cm - 1;
+                        while (cm != 0 && pick32(v, __ffs(cm) - 1) < thr_s) cm &= cm - 1;
                     }
                 }
             }
@@ -540,7 +550,7 @@ static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nl
     const bool pairs_ok = s->gemm_pairs && lreg != 0 && dbg_scores == nullptr;
     // shared memory: S pipeline stages + score staging (+ one list of Lc keys per query when the lists do not fit
     // in registers)
-    const size_t max_smem = 227 * 1024, fixed = 1024 + 512 + 4 * 32 * 33 * 4;
+    const size_t max_smem = 227 * 1024, fixed = 1024 + 512;
     const int Lp = (Lc + 1) & ~1;
     const size_t per_q = lreg != 0 ? 0 : (size_t)Lp * 8;
     int qpp = kGemmM;                                   // queries per single-CTA pass
@@ -562,6 +572,7 @@ static int gemm_passes(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nl
         int stages = (int)((max_smem - fixed - list_bytes) / stage_bytes);
         const int max_stages = pair ? kGemmStagesPair : kGemmStages;
         if (stages > max_stages) stages = max_stages;
+        if (s->gemm_stage_cap > 1 && stages > s->gemm_stage_cap) stages = s->gemm_stage_cap;
         // a hybrid batch whose sparse leg runs concurrently: leave ~64 KB of the SM's shared memory to its CTAs
         if (s->gemm_smem_reserve > 0)
             while (stages > 2 && fixed + (size_t)stages * stage_bytes + list_bytes + s->gemm_smem_reserve > max_smem) --stages;

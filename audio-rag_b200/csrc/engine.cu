@@ -556,6 +556,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_GEMM_FILTER")) s->gemm_filter = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_GEMM_PAIRS")) s->gemm_pairs = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_GEMM_L2_PREFETCH")) s->gemm_l2_prefetch = atoi(e) != 0;
+    if (const char* e = getenv("B200RAG_GEMM_STAGES")) s->gemm_stage_cap = atoi(e);
     if (const char* e = getenv("B200RAG_FUSED_TAIL")) s->fused_tail = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_OVERLAP_GEMM")) s->overlap_gemm = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);

@@ -127,6 +127,7 @@ struct Shard {
     bool gemm_pairs = true;               // knob: CTA pairs (cta_group::2, 256 queries per corpus pass) when > 128 queries remain
     bool gemm_l2_prefetch = false;        // knob (B200RAG_GEMM_L2_PREFETCH): corpus tiles prefetched into L2 one tile ahead
                                           // (measured SLOWER: 10M rows, B = 256 5.56 vs 4.79 ms, B = 128 5.78 vs 3.06 ms -- off)
+    int gemm_stage_cap = 0;               // knob (B200RAG_GEMM_STAGES): cap on the tcgen05 kernel's pipeline depth (0 = as many as fit)
     bool gemm_filter = true;              // knob: sample + filter path for tcgen05 batches with top-k beyond register lists
     int scan_shared = -1;                 // knob: SIMT scan selection: 0 = warp-private buffers, otherwise one CTA-shared buffer
     int dense_stage_cap = 0;              // 0 = as many ring stages as fit; set while a sparse CTA must co-reside
