@@ -66,6 +66,7 @@ SYMBOLS = [
     ("b200rag_set_stream", C.c_int, [_P, _P]),
     ("b200rag_set_slack", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_exhaustive", C.c_int, [_P, C.c_int32]),
+    ("b200rag_set_compression", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_exact_fallback", C.c_int, [_P, C.c_int32]),
     ("b200rag_set_pipeline", C.c_int, [_P, C.c_int32, _P]),
     ("b200rag_result_stream", C.c_void_p, [_P]),
@@ -297,6 +298,10 @@ class Shard:
     def set_exhaustive(self, on: bool):
         """Legs score EVERY eligible row canonically and sort: always exact (fallback + cross-check path)."""
         check(self._lib.b200rag_set_exhaustive(self._h, 1 if on else 0))
+
+    def set_compression(self, on: bool):
+        """Opt-in 8-bit copy of the rows for the candidate scan of 1-2 query searches (results stay exact)."""
+        check(self._lib.b200rag_set_compression(self._h, 1 if on else 0))
 
     def set_exact_fallback(self, on: bool):
         """Off: a search whose slack guard never clears raises B200RagError(ERR_INEXACT) instead of falling back."""

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200rag", "libb200rag.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["engine.cu", "dense_scan.cu", "dense_umma.cu", "select.cu", "sparse.cu", "synth.cu", "exact.cu", "group.cu"]
+SOURCES = ["engine.cu", "dense_scan.cu", "dense_umma.cu", "select.cu", "sparse.cu", "synth.cu", "exact.cu", "group.cu", "dense_q8.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "--cudart", "shared", "-ccbin", "g++"]

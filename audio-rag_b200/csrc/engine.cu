@@ -121,6 +121,18 @@ static int ensure_pinned(Shard* s, size_t bytes) {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// bring the 8-bit copy up to date with the rows stored (after appends: the new rows; after compaction / load: all)
+static int q8_sync_rows(Shard* s) {
+    if (!s->q8 || s->q8_rows == s->n_rows) return B200RAG_OK;
+    const size_t rb = (size_t)s->dim + 16;
+    if (s->q8_rows > s->n_rows) s->q8_rows = 0;
+    B2_TRY(s->dense_q8.ensure((size_t)std::max<int64_t>(s->n_rows, 1) * rb, (size_t)s->q8_rows * rb, s->stream));
+    B2_TRY(launch_quantize_rows(s, s->q8_rows, s->n_rows - s->q8_rows));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    s->q8_rows = s->n_rows;
+    return B200RAG_OK;
+}
+
 // ids_host: global ids of the new rows (strictly increasing, above every id stored so far) or nullptr = row_base + local
 static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
                        const float* w, int64_t nnz, bool host, const int64_t* ids_host, int dense_on_device = -1) {
@@ -174,6 +186,7 @@ static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t
     s->n_rows += n;
     s->nnz += nnz;
     s->last_id = new_last;
+    if (s->q8) B2_TRY(q8_sync_rows(s));
     return B200RAG_OK;
 }
 
@@ -255,6 +268,11 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // 1.25M, 10M and 12.5M rows, top-10 and top-100 (10M: 3.26 vs 3.36 ms per search).
     const bool use_gemm_path = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
 
+    // 8-bit candidate scan (opt-in, 1-2 queries per pass, first attempt only)
+    const bool use_q8 = s->q8 && want_dense && !use_gemm_path && s->slack == 0 && s->n_rows > 0 && s->q8_rows == s->n_rows &&
+                        leg_tail_fits(dense_scan_nlists(s), 3 * B200RAG_MAX_TOPK);
+    const int Lc_q8 = std::min(L + s->q8_slack, 3 * B200RAG_MAX_TOPK);
+
     // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
     const int nl_scan = dense_scan_nlists(s);
     // (only while the tails are light, i.e. up to 64 candidates per leg: the tails of search i run beside the dense scan
@@ -262,7 +280,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     //  re-score -- holds back the SM it shares and with it the whole scan: 12.5M rows, top-100: 4.37 ms per step pipelined,
     //  4.19 ms in the classic form.  Claiming tiles dynamically instead costs more than it saves: B200RAG_SCAN_DYNAMIC.)
     const bool piped = s->pipeline && !s->pipeline_paused && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
-                       Lc <= 64 && leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
+                       !use_q8 && Lc <= 64 && leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
     if (piped) {
         cudaStream_t sd = s->pipe_stream;
         const int par = (int)(s->legs_calls & 1);                 // (legs_calls was incremented by the caller)
@@ -356,6 +374,20 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_TRY(s->ws.lists_b.ensure((size_t)B * nl_max * Lc * 8, 0, st));
             int nlists = 0;
             const bool use_gemm = s->dense_path == 2 || (s->dense_path == 0 && B > 2);
+            if (use_q8) {
+                // 8-bit candidate scan: half the bytes, upper-bound keys, a wider candidate set (the rows inside the
+                // quantisation error band), then the usual exact re-score from the bf16 rows.  A retry (slack != 0)
+                // never comes here: it takes the bf16 scan.
+                B2_TRY(s->ws.lists_a.ensure((size_t)B * nl_max * Lc_q8 * 8, 0, st));
+                B2_TRY(s->ws.exact.ensure((size_t)B * Lc_q8 * 8, 0, st));
+                s->dense_stage_cap = s->dense_stage_cap_env;
+                const int rcq = launch_dense_scan_q8(s, B, Lc_q8, s->ws.lists_a.as<uint64_t>(), &nlists);
+                s->dense_stage_cap = 0;
+                if (rcq != B200RAG_OK) return rcq;
+                const int dthr_q = q.has_threshold && q.mode == B200RAG_DENSE;
+                B2_TRY(launch_leg_tail(s, false, B, nlists, Lc_q8, L, s->ws.lists_a.as<uint64_t>(), 1e-7f, 0.f, nullptr, dthr_q,
+                                       q.score_threshold, out, ambiguous, s->ws.thr.as<uint64_t>()));
+            } else {
             s->dense_stage_cap = s->dense_stage_cap_env;   // (3 x 32 KB leaves room for a co-resident sparse CTA too)
             uint64_t* approx = nullptr;
             // tcgen05 path with a top-k too large for register lists: sample + filter (128 queries per pass whatever
@@ -384,6 +416,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
                 B2_TRY(launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
                                            q.score_threshold, out, ambiguous));
             }
+            }   // !use_q8
         }
     }
     if (want_sparse) {
@@ -561,6 +594,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_OVERLAP_GEMM")) s->overlap_gemm = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
+    if (const char* e = getenv("B200RAG_Q8_SLACK")) { const int v = atoi(e); if (v > 0) s->q8_slack = v; }
     if (const char* e = getenv("B200RAG_SCAN_DYNAMIC")) s->scan_dynamic = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SCAN_CTAS")) s->scan_ctas = atoi(e);
     if (const char* e = getenv("B200RAG_EXACT_FALLBACK")) s->exact_fallback = atoi(e) != 0;
@@ -589,7 +623,7 @@ void b200rag_shard_destroy(b200rag_shard* sp) {
     if (s->side_stream) cudaStreamSynchronize(s->side_stream);
     if (s->pipeline && s->pipe_stream) cudaStreamSynchronize(s->pipe_stream);
     p2p_release(s);
-    s->dense.release(); s->row_ids.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
+    s->dense.release(); s->dense_q8.release(); s->row_ids.release(); s->fwd_ptr.release(); s->fwd_terms.release(); s->fwd_w.release();
     s->ws.ex_keys.release(); s->ws.ex_sorted.release(); s->ws.ex_temp.release();
     s->dir.release(); s->blk_base.release(); s->post_doc.release(); s->post_w.release();
     for (auto& kv : s->masks) kv.second.release();
@@ -627,6 +661,22 @@ int b200rag_set_slack(b200rag_shard* sp, int32_t slack) {
     if (s == nullptr || slack < 0) { set_error("set_slack: bad argument"); return B200RAG_ERR_INVALID; }
     s->slack = slack;
     return B200RAG_OK;
+}
+
+int b200rag_set_compression(b200rag_shard* sp, int32_t on) {
+    Shard* s = (Shard*)sp;
+    if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
+    B2_TRY(use_device(s));
+    B2_TRY(sync_all(s));
+    if (!on) {
+        s->q8 = false;
+        s->q8_rows = 0;
+        s->dense_q8.release();
+        return B200RAG_OK;
+    }
+    if (!dense_q8_supported(s)) { set_error("set_compression: the 8-bit scan needs dim 512 or 1024"); return B200RAG_ERR_INVALID; }
+    s->q8 = true;
+    return q8_sync_rows(s);
 }
 
 int b200rag_set_exhaustive(b200rag_shard* sp, int32_t on) {
@@ -785,7 +835,8 @@ int b200rag_compact(b200rag_shard* sp, const uint32_t* keep_words, int64_t n_row
     s->masks.clear(); s->mask_rows.clear();
     s->staged = false;
     for (auto& sl : s->slots) sl.staged = false;
-    return B200RAG_OK;
+    s->q8_rows = 0;                      // local rows moved: the 8-bit copy is rebuilt from the bf16 rows
+    return q8_sync_rows(s);
 }
 
 int b200rag_build(b200rag_shard* sp) {
@@ -806,6 +857,7 @@ int b200rag_clear(b200rag_shard* sp) {
     s->n_rows = 0; s->nnz = 0; s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0;
     s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->last_id = INT64_MIN;
+    s->q8_rows = 0;
     B2_CUDA(cudaMemsetAsync(s->fwd_ptr.p, 0, 8, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
     s->h_blk_base.clear();
@@ -1316,6 +1368,8 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
     s->last_id = last_id;
     s->built_rows = 0; s->n_blocks = 0; s->inv_nnz = 0; s->w_absmax = 0.f; s->wmax_nnz = 0;
     s->h_blk_base.clear();
+    s->q8_rows = 0;
+    B2_TRY(q8_sync_rows(s));
     return build_inverted(s);
 }
 

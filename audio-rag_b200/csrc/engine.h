@@ -154,6 +154,11 @@ struct Shard {
     // dense rows
     int64_t n_rows = 0;
     DevBuf dense;  // [n_rows, dim] bf16 bits
+    // optional 8-bit copy of the rows for the candidate scan (dense_q8.cu): [n_rows][dim + 16] int8 values + {scale, l1}
+    DevBuf dense_q8;
+    bool q8 = false;              // b200rag_set_compression
+    int64_t q8_rows = 0;          // rows quantised so far (== n_rows whenever q8 is on)
+    int q8_slack = 364;           // extra candidates of the 8-bit scan: rows inside its error band (knob B200RAG_Q8_SLACK)
     DevBuf row_ids;               // i64 [n_rows] global id of every local row, strictly increasing (R1, R5)
     int64_t last_id = INT64_MIN;  // largest id stored so far
 
@@ -216,6 +221,13 @@ struct Shard {
 // SIMT bulk-copy scan: approximate fp32 scores, per-CTA top-Lc key lists.  Returns number of lists per query.
 int launch_dense_scan(Shard* s, int batch, int Lc, uint64_t* out_lists /*[batch, nlists, Lc]*/, int* nlists);
 int dense_scan_nlists(const Shard* s);
+
+// ---- dense_q8.cu ----------------------------------------------------------------------------------------
+// 8-bit candidate scan (opt-in): quantise rows [row0, row0 + n) of s->dense into s->dense_q8; scan = launch_dense_scan with
+// upper-bound keys (a row outside the retained candidates scores at most the weakest retained key: guard eps = 0)
+bool dense_q8_supported(const Shard* s);
+int launch_quantize_rows(Shard* s, int64_t row0, int64_t n);
+int launch_dense_scan_q8(Shard* s, int batch, int Lc, uint64_t* out_lists, int* nlists);
 
 // ---- dense_umma.cu --------------------------------------------------------------------------------------
 // tcgen05 + TMA GEMM with the top-k fused in the TMEM epilogue (<= 128 queries per corpus pass). Same output format.

@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-oracle-check", action="store_true", help="skip the full-corpus oracle check (profiling runs)")
+    ap.add_argument("--compressed", action="store_true",
+                    help="opt-in 8-bit candidate scan (b200rag_set_compression): NOT the headline configuration")
     return ap.parse_args()
 
 
@@ -283,6 +285,8 @@ def build_shard(a, dev, lo, hi):
         del bits
     if sparse:
         sh.build()
+    if a.compressed:
+        sh.set_compression(True)
     torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()
     return sh
@@ -538,6 +542,8 @@ def run_b200(a):
                 traffic = None
         rows_rank = hi - lo
         algo_gb = rows_rank * a.dim * 2 / 1e9
+        if dense_path == 3:      # the 8-bit candidate scan reads (dim + 16) bytes per row
+            algo_gb = rows_rank * (a.dim + 16) / 1e9
         # the dominant kernel: SIMT bulk scan (1-2 queries, one launch per corpus pass) or the tcgen05 GEMM (batches:
         # one launch per pass of <= 256 queries).  Per-launch figures: bytes = rows * dim * 2, flops = 2 * q * rows * dim.
         passes = max(int(dense_passes), 1)
@@ -561,7 +567,11 @@ def run_b200(a):
                 roof.update({"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
                              "frac": tflops / tf_peak,
                              "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"})
-        roof.update({"algorithmic_bytes_per_launch": int(rows_rank * a.dim * 2), "launches_per_step": passes,
+        if dense_path == 3:
+            roof["kernel"] = "dense_scan_q8_kernel (opt-in 8-bit candidate scan + exact re-score from the bf16 rows)"
+            roof["traffic"] = None
+            roof["bf16_equivalent_GBps"] = rows_rank * a.dim * 2 / 1e9 / (launch_ms / 1e3) if dense_k_ms > 0 else 0.0
+        roof.update({"algorithmic_bytes_per_launch": int(algo_gb * 1e9), "launches_per_step": passes,
                      "kernel_ms": launch_ms, "kernel_share_of_step": dense_k_ms / (total_ms / K),
                      "sparse_scan_ms": sparse_k_ms, "sparse_postings_per_step": int(postings),
                      "sparse_algorithmic_GBps": postings * 6 / 1e9 / (sparse_k_ms / 1e3) if sparse_k_ms > 0 else 0.0,
@@ -571,8 +581,8 @@ def run_b200(a):
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": workload(a, world),
+            "dtype": "bf16" if dense_path != 3 else "bf16 (exact re-score) after an int8 candidate scan", "data": "synthetic",
+            "config": workload(a, world) if not a.compressed else {**workload(a, world), "compressed_candidate_scan": True},
             "exchange": ("CUDA-IPC peer windows (NVLink stores + epoch flags)" + (", pipelined tail" if ss.pipeline else "")
                          if ss.p2p else "NCCL all-gather") if world > 1 else None,
             "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),

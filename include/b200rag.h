@@ -107,6 +107,13 @@ int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximat
  *                          B200RAG_ERR_INEXACT instead of returning a result whose guard never cleared
  *                          (default 1; the environment variable B200RAG_EXACT_FALLBACK=0 sets the default to 0). */
 int b200rag_set_exhaustive(b200rag_shard* s, int32_t on);
+/* Corpus compression for the candidate scan (opt-in, dim 512 or 1024).  The shard keeps an 8-bit copy
+ * of its rows ([n][dim + 16]: symmetric int8 per row + scale) beside the bf16 rows; searches of 1-2 queries scan THAT
+ * (half the bytes), ranking rows by a rigorous UPPER BOUND of their exact score, keep a wider candidate set (the rows
+ * inside the quantisation error band: `B200RAG_Q8_SLACK`, default 364 extra candidates) and re-score the candidates
+ * exactly from the bf16 rows -- ids and scores stay bit-identical to the uncompressed path; when the guard does not clear,
+ * the retry scans the bf16 rows.  Costs (dim + 16) bytes per row of HBM.  Maintained through add / compact / load. */
+int b200rag_set_compression(b200rag_shard* s, int32_t on);
 int b200rag_set_exact_fallback(b200rag_shard* s, int32_t on);
 /* Pipelined searches (throughput mode for callers that enqueue search after search on staged batches: b200rag_legs ->
  * [b200rag_p2p_exchange ->] b200rag_fuse / b200rag_p2p_fuse, no host synchronisation in between).  With pipeline on, ONLY
@@ -275,8 +282,8 @@ int b200rag_group_search(b200rag_group* g, const b200rag_query* q, int64_t* out_
 /* Counters of the last `legs` call, for bench.py's gpu_launches / roofline bookkeeping. */
 typedef struct {
     int32_t kernel_launches;     /* kernels of this library launched by the last legs+fuse               */
-    int32_t dense_path;          /* 0 = none, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM                    */
-    int64_t dense_bytes;         /* algorithmic bytes of the dense leg (rows * dim * 2 per corpus pass)   */
+    int32_t dense_path;          /* 0 = none, 1 = SIMT bulk-copy scan, 2 = tcgen05 GEMM, 3 = 8-bit SIMT scan */
+    int64_t dense_bytes;         /* algorithmic bytes of the dense leg (rows * dim * 2 per corpus pass; rows * (dim + 16) for the 8-bit scan) */
     int64_t sparse_postings;     /* postings of the query terms in this shard (sum over batch)            */
     int32_t dense_passes;        /* corpus passes made for the batch                                      */
     int32_t retries;             /* slack-guard retries inside b200rag_search                              */
