@@ -5,12 +5,16 @@
 // for 1-2 queries per corpus pass.  The result is still EXACT: this kernel only selects candidates; they are re-scored
 // from the bf16 rows in the canonical order (select.cu) and the guard below is rigorous.
 //
-// Format: row r = 1024 (dim) int8 values q_i + trailer {f32 scale, f32 l1, 8 bytes pad}: x_i ~ scale * q_i with
-// |x_i - scale * q_i| <= 0.5 * scale (symmetric, round to nearest, scale = max|x_i| / 127), l1 = scale * sum|q_i|.
+// Format: row r = 1024 (dim) int8 values q_i + trailer {f32 scale, f32 l1, f32 e2, 4 bytes pad}: x_i ~ scale * q_i with
+// |x_i - scale * q_i| <= 0.5 * scale (symmetric, round to nearest, scale = max|x_i| / 127), l1 = scale * sum|q_i|,
+// e2 = ||x - scale * q||_2, the row's MEASURED quantisation residual.
 // The query is quantised to 14-bit integers in the kernel's prologue (qs = max|y_i| / 8191), so a row's score is ONE
 // exact integer dot product (dp2a: 16-bit x 8-bit multiply-accumulates, |sum| <= 1024 * 8191 * 127 < 2^31):
 //     s^ = scale * qs * sum_i q_i * yq_i
-//     |s - s^| <= 0.5 * scale * ||y||_1  +  0.5 * qs * l1  (+ fp32 rounding of two products)
+//     s - s^ = sum_i (x_i - scale q_i) y_i  +  sum_i scale q_i (y_i - qs yq_i)
+//     |s - s^| <= min(0.5 * scale * ||y||_1, e2 * ||y||_2)  +  0.5 * qs * l1  (+ fp32 rounding of the products)
+// (Hoelder and Cauchy-Schwarz on the first sum; the second is the tighter one on typical rows -- e2 ~ scale * sqrt(dim / 12)
+//  against 0.5 * scale * ||y||_1 ~ 0.4 * scale * sqrt(dim) -- and the band it leaves holds about half as many rows.)
 // The kernel ranks rows by the UPPER BOUND  ub = s^ + err(row): a row that is not among the Lc retained candidates has
 // exact score <= ub <= the weakest retained ub, so the leg is exact as soon as that weakest ub is below the L-th exact
 // score -- the same guard as for the bf16 scan, with eps = 0 and a larger slack (typically ~250 rows fall inside the
@@ -61,19 +65,26 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const uint16_t* __re
     const float scale = m > 0.f ? m / 127.f : 1.f;
     const float inv = 1.f / scale;
     int l1 = 0;
+    float e2 = 0.f;
     for (int k = lane; k < dim; k += 32) {
-        int v = __float2int_rn(__uint_as_float((uint32_t)src[k] << 16) * inv);
+        const float x = __uint_as_float((uint32_t)src[k] << 16);
+        int v = __float2int_rn(x * inv);
         v = v > 127 ? 127 : (v < -127 ? -127 : v);
         dst[k] = (uint8_t)(int8_t)v;
         l1 += v < 0 ? -v : v;
+        const float e = fmaf(-scale, (float)v, x);      // x - scale * v, rounded once
+        e2 = fmaf(e, e, e2);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+    for (int d = 16; d > 0; d >>= 1) {
+        l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, d);
+    }
     if (lane == 0) {
         float* tr = reinterpret_cast<float*>(dst + dim);
         tr[0] = scale;
         tr[1] = scale * (float)l1 * 1.0001f;
-        tr[2] = 0.f;
+        tr[2] = sqrtf(e2) * 1.0001f;                     // (1e-4 covers the fp32 roundings of the residuals and their sum)
         tr[3] = 0.f;
     }
 }
@@ -158,11 +169,11 @@ __global__ void __launch_bounds__(kQ8Threads, 1) dense_scan_q8_kernel(const Dens
 
     // query -> 14-bit integers, element pairs packed for dp2a: lane owns bytes [c * 512 + lane * 16, +16) of a row, c < NW16
     int qp[NQ][NW16 * 8];            // 16 elements per chunk = 8 packed pairs
-    float qs[NQ], ql1[NQ];
+    float qs[NQ], ql1[NQ], ql2[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         float y[NW16 * 16];
-        float m = 0.f, l1 = 0.f;
+        float m = 0.f, l1 = 0.f, l2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NW16; ++c) {
             const uint4 a = *reinterpret_cast<const uint4*>(p.q_bits + (size_t)q * DIM + c * 512 + lane * 16);
@@ -175,16 +186,18 @@ __global__ void __launch_bounds__(kQ8Threads, 1) dense_scan_q8_kernel(const Dens
             }
         }
 #pragma unroll
-        for (int i = 0; i < NW16 * 16; ++i) { m = fmaxf(m, fabsf(y[i])); l1 += fabsf(y[i]); }
+        for (int i = 0; i < NW16 * 16; ++i) { m = fmaxf(m, fabsf(y[i])); l1 += fabsf(y[i]); l2 = fmaf(y[i], y[i], l2); }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
             l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+            l2 += __shfl_xor_sync(0xffffffffu, l2, d);
         }
         const float sc = m > 0.f ? m / 8191.f : 1.f;
         const float inv = 1.f / sc;
         qs[q] = sc;
         ql1[q] = l1 * 1.0001f;                        // (the fp32 sum of 1024 magnitudes: 1e-4 covers its rounding)
+        ql2[q] = sqrtf(l2) * 1.0001f;
 #pragma unroll
         for (int i = 0; i < NW16 * 8; ++i) {
             int lo = __float2int_rn(y[2 * i] * inv), hi = __float2int_rn(y[2 * i + 1] * inv);
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(kQ8Threads, 1) dense_scan_q8_kernel(const Dens
 
         // this warp's rows: cw, cw + 8, cw + 16, cw + 24
         uint4 v[ROWS_PER_WARP][NW16];
-        float rscale[ROWS_PER_WARP], rl1[ROWS_PER_WARP];
+        float rscale[ROWS_PER_WARP], rl1[ROWS_PER_WARP], re2[ROWS_PER_WARP];
 #pragma unroll
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
             const int rr = cw + r * kScanConsumerWarps;
@@ -240,9 +253,10 @@ __global__ void __launch_bounds__(kQ8Threads, 1) dense_scan_q8_kernel(const Dens
 #pragma unroll
             for (int c = 0; c < NW16; ++c)
                 v[r][c] = has ? *reinterpret_cast<const uint4*>(rp + c * 512 + lane * 16) : make_uint4(0, 0, 0, 0);
-            const float2 tr = has ? *reinterpret_cast<const float2*>(rp + DIM) : make_float2(0.f, 0.f);
+            const float4 tr = has ? *reinterpret_cast<const float4*>(rp + DIM) : make_float4(0.f, 0.f, 0.f, 0.f);
             rscale[r] = tr.x;
             rl1[r] = tr.y;
+            re2[r] = tr.z;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
@@ -284,7 +298,8 @@ __global__ void __launch_bounds__(kQ8Threads, 1) dense_scan_q8_kernel(const Dens
                 if (rr >= rows) continue;
                 const float sh = rscale[r] * qs[q] * (float)dot[q][r];
                 // rigorous upper bound of the exact score (see the header); fp32 slack on top
-                const float ub = sh + kQ8Half * (rscale[r] * ql1[q] + qs[q] * rl1[r]) + 4e-7f * fabsf(sh) + 1e-7f;
+                const float erow = fminf(kQ8Half * rscale[r] * ql1[q], re2[r] * ql2[q]);
+                const float ub = sh + erow + kQ8Half * qs[q] * rl1[r] + 4e-7f * fabsf(sh) + 1e-7f;
                 const uint32_t row = (uint32_t)(row0 + rr);
                 const uint64_t key = make_key(ub + 0.0f, row);
                 if (key > thr[q]) {                   // warp-uniform

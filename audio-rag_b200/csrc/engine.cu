@@ -137,6 +137,7 @@ static int q8_sync_rows(Shard* s) {
 static int append_rows(Shard* s, int64_t n, const uint16_t* dense, const int64_t* indptr, const uint32_t* terms,
                        const float* w, int64_t nnz, bool host, const int64_t* ids_host, int dense_on_device = -1) {
     cudaStream_t st = s->stream;
+    B2_TRY(sync_all(s));               // (pipelined mode: tails still in flight read the buffers that grow below)
     const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;   // CSR arrays
     const cudaMemcpyKind dkind = (dense_on_device < 0 ? !host : dense_on_device != 0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const size_t row_bytes = (size_t)s->dim * 2;
@@ -271,7 +272,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     // 8-bit candidate scan (opt-in, 1-2 queries per pass, first attempt only)
     const bool use_q8 = s->q8 && want_dense && !use_gemm_path && s->slack == 0 && s->n_rows > 0 && s->q8_rows == s->n_rows &&
                         leg_tail_fits(dense_scan_nlists(s), 3 * B200RAG_MAX_TOPK);
-    const int Lc_q8 = std::min(L + s->q8_slack, 3 * B200RAG_MAX_TOPK);
+    // (the error band of the upper bounds holds a multiple of L rows: a few dozen at top-10, several hundred at top-100)
+    const int Lc_q8 = std::min(L + std::max(s->q8_slack, 3 * L), 3 * B200RAG_MAX_TOPK);
 
     // ---- pipelined form: the SIMT scan alone on the main stream, everything else on the side stream -------------
     const int nl_scan = dense_scan_nlists(s);
@@ -280,7 +282,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
     //  re-score -- holds back the SM it shares and with it the whole scan: 12.5M rows, top-100: 4.37 ms per step pipelined,
     //  4.19 ms in the classic form.  Claiming tiles dynamically instead costs more than it saves: B200RAG_SCAN_DYNAMIC.)
     const bool piped = s->pipeline && !s->pipeline_paused && s->pipe_stream != nullptr && s->fused_tail && !use_gemm_path && s->n_rows > 0 &&
-                       !use_q8 && Lc <= 64 && leg_tail_fits(nl_scan, Lc) && (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
+                       (!use_q8 || (s->q8_pipeline && leg_tail_fits(nl_scan, Lc_q8))) && Lc <= 64 && leg_tail_fits(nl_scan, Lc) &&
+                       (!want_sparse || leg_tail_fits(sparse_scan_nlists(s, B, Lc), Lc));
     if (piped) {
         cudaStream_t sd = s->pipe_stream;
         const int par = (int)(s->legs_calls & 1);                 // (legs_calls was incremented by the caller)
@@ -289,8 +292,9 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         b200rag_cand* out_sparse = cands + (want_dense ? (size_t)B * L : 0);
         const bool sparse_live = want_sparse && s->nnz > 0 && s->staged_q_terms > 0;
         int nlists = 0;
+        const int Lc_d = use_q8 ? Lc_q8 : Lc;                     // candidates per list of the dense leg
         if (want_dense) {
-            B2_TRY(lists.ensure((size_t)B * nl_scan * Lc * 8, 0, st));
+            B2_TRY(lists.ensure((size_t)B * nl_scan * Lc_d * 8, 0, st));
             if (s->ev_tail_rec[par]) B2_CUDA(cudaStreamWaitEvent(st, s->ev_tail[par], 0));
             B2_CUDA(cudaMemsetAsync(s->ws.thr.as<uint64_t>() + (size_t)par * 2 * B, 0, (size_t)2 * B * 8, st));
         }
@@ -300,7 +304,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
         if (want_dense) {
             s->dense_stage_cap = s->dense_stage_cap_env;
             s->thr_par = par;
-            const int rc = launch_dense_scan(s, B, Lc, lists.as<uint64_t>(), &nlists);
+            const int rc = use_q8 ? launch_dense_scan_q8(s, B, Lc_d, lists.as<uint64_t>(), &nlists)
+                                  : launch_dense_scan(s, B, Lc, lists.as<uint64_t>(), &nlists);
             s->thr_par = 0;
             s->dense_stage_cap = 0;
             if (rc != B200RAG_OK) return rc;
@@ -332,8 +337,8 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             cudaError_t e = cudaStreamWaitEvent(sd, s->ev_scan[par], 0);
             if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent(scan)");
             const int dthr = q.has_threshold && q.mode == B200RAG_DENSE;
-            if (rc == B200RAG_OK) rc = launch_leg_tail(s, false, B, nlists, Lc, L, lists.as<uint64_t>(), 6.5e-5f, 0.f, nullptr, dthr,
-                                                       q.score_threshold, out_dense, ambiguous,
+            if (rc == B200RAG_OK) rc = launch_leg_tail(s, false, B, nlists, Lc_d, L, lists.as<uint64_t>(), use_q8 ? 1e-7f : 6.5e-5f,
+                                                       0.f, nullptr, dthr, q.score_threshold, out_dense, ambiguous,
                                                        s->ws.thr.as<uint64_t>() + (size_t)par * 2 * B);
             if (rc == B200RAG_OK) {
                 e = cudaEventRecord(s->ev_tail[par], sd);
@@ -595,6 +600,7 @@ int b200rag_shard_create(const b200rag_config* cfg, b200rag_shard** out) {
     if (const char* e = getenv("B200RAG_SPARSE_THREADS")) s->sparse_threads = atoi(e);
     if (const char* e = getenv("B200RAG_SPARSE_BPC")) s->sparse_bpc = atoi(e);
     if (const char* e = getenv("B200RAG_Q8_SLACK")) { const int v = atoi(e); if (v > 0) s->q8_slack = v; }
+    if (const char* e = getenv("B200RAG_Q8_PIPELINE")) s->q8_pipeline = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SCAN_DYNAMIC")) s->scan_dynamic = atoi(e) != 0;
     if (const char* e = getenv("B200RAG_SCAN_CTAS")) s->scan_ctas = atoi(e);
     if (const char* e = getenv("B200RAG_EXACT_FALLBACK")) s->exact_fallback = atoi(e) != 0;
@@ -822,6 +828,7 @@ int b200rag_compact(b200rag_shard* sp, const uint32_t* keep_words, int64_t n_row
     if (n_rows_mask != s->n_rows) { set_error("compact: the keep mask must cover exactly the shard's rows"); return B200RAG_ERR_INVALID; }
     if (s->n_rows == 0) return B200RAG_OK;
     B2_TRY(use_device(s));
+    B2_TRY(sync_all(s));
     const size_t words = (size_t)((s->n_rows + 31) / 32);
     DevBuf km;
     B2_TRY(km.ensure(words * 4, 0, s->stream));
@@ -843,6 +850,7 @@ int b200rag_build(b200rag_shard* sp) {
     Shard* s = (Shard*)sp;
     if (s == nullptr) { set_error("null shard"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
+    B2_TRY(sync_all(s));
     return build_inverted(s);
 }
 
@@ -1299,7 +1307,7 @@ extern "C" int b200rag_save(b200rag_shard* sp, const char* path) {
     Shard* s = (Shard*)sp;
     if (s == nullptr || path == nullptr) { set_error("save: null argument"); return B200RAG_ERR_INVALID; }
     B2_TRY(use_device(s));
-    B2_CUDA(cudaStreamSynchronize(s->stream));
+    B2_TRY(sync_all(s));
     FILE* f = fopen(path, "wb");
     if (f == nullptr) { set_error(std::string("save: cannot open ") + path); return B200RAG_ERR_INVALID; }
     ShardFileHeader h{};
@@ -1323,6 +1331,7 @@ extern "C" int b200rag_load(b200rag_shard* sp, const char* path) {
     if (s == nullptr || path == nullptr) { set_error("load: null argument"); return B200RAG_ERR_INVALID; }
     if (s->n_rows != 0) { set_error("load: the shard must be empty"); return B200RAG_ERR_STATE; }
     B2_TRY(use_device(s));
+    B2_TRY(sync_all(s));
     FILE* f = fopen(path, "rb");
     if (f == nullptr) { set_error(std::string("load: cannot open ") + path); return B200RAG_ERR_INVALID; }
     ShardFileHeader h{};

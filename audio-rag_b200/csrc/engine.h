@@ -154,11 +154,12 @@ struct Shard {
     // dense rows
     int64_t n_rows = 0;
     DevBuf dense;  // [n_rows, dim] bf16 bits
-    // optional 8-bit copy of the rows for the candidate scan (dense_q8.cu): [n_rows][dim + 16] int8 values + {scale, l1}
+    // optional 8-bit copy of the rows for the candidate scan (dense_q8.cu): [n_rows][dim + 16] int8 values + {scale, l1, e2}
     DevBuf dense_q8;
     bool q8 = false;              // b200rag_set_compression
     int64_t q8_rows = 0;          // rows quantised so far (== n_rows whenever q8 is on)
-    int q8_slack = 364;           // extra candidates of the 8-bit scan: rows inside its error band (knob B200RAG_Q8_SLACK)
+    int q8_slack = 236;           // extra candidates of the 8-bit scan: rows inside its error band, at least 3 L (knob B200RAG_Q8_SLACK)
+    bool q8_pipeline = false;     // 8-bit scan in the pipelined form too (knob B200RAG_Q8_PIPELINE)
     DevBuf row_ids;               // i64 [n_rows] global id of every local row, strictly increasing (R1, R5)
     int64_t last_id = INT64_MIN;  // largest id stored so far
 

@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-oracle-check", action="store_true", help="skip the full-corpus oracle check (profiling runs)")
+    ap.add_argument("--no-compressed-leg", action="store_true",
+                    help="skip the extra (non-headline) measurement of the opt-in 8-bit candidate scan")
     ap.add_argument("--compressed", action="store_true",
                     help="opt-in 8-bit candidate scan (b200rag_set_compression): NOT the headline configuration")
     return ap.parse_args()
@@ -519,13 +521,59 @@ def run_b200(a):
     except Exception as e:
         ocheck = {"queries": 0, "mismatches": None, "error": repr(e)}
 
+    # ------------------------------------------------------------------ (5) the opt-in 8-bit candidate scan, same steps
+    # NOT the headline: the same staged steps once more with b200rag_set_compression on (candidates from an int8 copy of
+    # the rows, exact re-score from the bf16 rows).  Both paths are exact, so the last step must return the same bytes.
+    q8, q8_ms, q8_dense_ms = None, 0.0, 0.0
+    if not a.compressed and not a.no_compressed_leg and B <= 2 and a.dim in (512, 1024) and a.mode != "sparse":
+        ok = 1.0
+        try:
+            sh.set_compression(True)
+        except Exception as e:
+            ok, q8 = 0.0, {"value": None, "error": repr(e)}
+        if world > 1:                                 # every rank or none: the exchange waits on all of them
+            okt = torch.tensor([ok], dtype=torch.float64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            ok = float(okt.item())
+        if ok > 0:
+            try:
+                sh.set_profiling(True)
+                barrier()
+                for i in range(W):
+                    ss.use_slot(i % n_slots)
+                    b8 = ss.run_staged()
+                barrier()
+                q_begin, q_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q_begin.record()
+                for i in range(W, nsteps):
+                    ss.use_slot(i % n_slots)
+                    b8 = ss.run_staged()
+                ss.record_end(q_end)
+                barrier()
+                q8_ms = float(q_begin.elapsed_time(q_end))
+                st8 = sh.stats()
+                d8 = [sh.stats_step(j)["dense_scan_ms"] for j in range(min(K, 64))]
+                q8_dense_ms = float(np.mean(d8))
+                ids8, sc8, cnt8, amb8 = ss.fetch(b8)
+                sh.set_profiling(False)
+                q8 = {"dense_path": int(st8["dense_path"]), "ambiguous_flags": int(amb8),
+                      "matches_bf16_path": bool(np.array_equal(ids8, ids_dev) and np.array_equal(sc8, sc_dev)),
+                      "scan_bytes_per_rank": int(st8["dense_bytes"])}
+            except Exception as e:
+                q8 = {"value": None, "error": repr(e)}
+        try:
+            sh.set_compression(False)
+        except Exception:
+            pass
+
     # ------------------------------------------------------------------ reduce over ranks (MAX)
     red = torch.tensor([total_ms, e2e_total, float(np.mean(dense_ms)), float(np.mean(sparse_ms)), wall_value,
-                        copies_ms, float(np.mean(pre_ms)), float(np.mean(tail_ms))],
+                        copies_ms, float(np.mean(pre_ms)), float(np.mean(tail_ms)), q8_ms, q8_dense_ms],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total, dense_k_ms, sparse_k_ms, wall_value, copies_ms, pre_max, tail_max = [float(x) for x in red.tolist()]
+    (total_ms, e2e_total, dense_k_ms, sparse_k_ms, wall_value, copies_ms, pre_max, tail_max, q8_ms,
+     q8_dense_ms) = [float(x) for x in red.tolist()]
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -608,6 +656,18 @@ def run_b200(a):
             "clocks": clocks,
             "build_s": t_build, "ambiguous_flags": int(amb),
         }
+        if q8 is not None:
+            if q8_ms > 0 and "error" not in q8:
+                q8_bytes = rows_rank * (a.dim + 16)
+                q8.update({"value": B * K / (q8_ms / 1e3), "unit": "queries/s", "ms_per_step": q8_ms / K,
+                           "dense_scan_ms": q8_dense_ms,
+                           "scan_GBps": q8_bytes / 1e9 / (q8_dense_ms / 1e3) if q8_dense_ms > 0 else None,
+                           "scan_frac_of_hbm_peak": q8_bytes / 1e9 / (q8_dense_ms / 1e3) / peak if q8_dense_ms > 0 else None,
+                           "note": "opt-in (b200rag_set_compression): candidates from an int8 copy of the rows (dim + 16 bytes "
+                                   "per row), ranked by a rigorous upper bound, then the same exact fp64 re-score from the "
+                                   "bf16 rows as the headline path; device-resident timing like `value`, max over ranks; "
+                                   "costs (dim + 16) bytes of HBM per row on top of the bf16 rows"})
+            line["compressed_candidate_scan"] = q8
         if world == 1 and not a.no_cpu_baseline:
             try:
                 _, detail, _ = cpu_reference(a, a.cpu_queries, 2, a.cpu_sample_rows)
