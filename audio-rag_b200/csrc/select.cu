@@ -346,10 +346,18 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
     // it.  The scans' own grid-wide threshold (p.gkey: the Lc-th best key of SOME list) is a second valid bound -- a much
     // weaker one (at 10M rows it let 12 000 of 31 700 keys through where the maxima let ~100 through), but the only one
     // when Lc exceeds 32 keys per warp -- so the tighter of the two is used.
+    // (The lists are SORTED: with a plain stride of NT a thread would meet the same rank of every list whenever Lc divides
+    //  NT -- Lc = 256: thread t only ever sees rank t mod 256 -- the maxima would be stratified by rank, the threshold as
+    //  weak as the lists' tails, and nearly every key would survive: 250 us of radix select instead of 60 us.  Rotating
+    //  the lane assignment by 37 slots per round gives every thread a spread of ranks and keeps the loads coalesced.)
     uint64_t tmax = 0;
-    for (int i = tid; i < total; i += NT) {            // (independent loads: the compiler batches them)
-        const uint64_t k = src[i];
-        tmax = k > tmax ? k : tmax;
+    {
+        int j = 0;
+        for (int base = 0; base < total; base += NT, ++j) {   // (independent loads: the compiler batches them)
+            const int i = base + ((tid + 37 * j) & (NT - 1));
+            const uint64_t k = i < total ? src[i] : 0ull;
+            tmax = k > tmax ? k : tmax;
+        }
     }
     {
         uint64_t v = tmax;
@@ -595,6 +603,17 @@ __device__ __forceinline__ b200rag_cand ld_cand_cg(const b200rag_cand* p) {
     return c;
 }
 
+// 1 if some shard's block of `stage` ([n_shards][L]) is not in leg order (valid first, then cand_better); per thread
+__device__ __forceinline__ int block_unsorted(const b200rag_cand* stage, int M, int L) {
+    int bad = 0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        if (i % L == 0) continue;
+        const b200rag_cand e = stage[i], pv = stage[i - 1];
+        if (e.valid && !(pv.valid && cand_better(pv, e))) bad = 1;
+    }
+    return bad;
+}
+
 // smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
 __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
                                                    int64_t shard_stride, int has_trailer, int nlegs, int batch,
@@ -681,6 +700,32 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
                 for (int f = 0; f < M; ++f) {
                     const b200rag_cand o = stage[f];
                     if (o.valid && cand_better(o, e)) ++rank;
+                }
+                if (rank < L) { leg_id[leg * L + rank] = e.id; leg_score[leg * L + rank] = e.score; }
+            }
+            if (local) atomicAdd(&leg_n[leg], local);
+        } else if (__syncthreads_or(block_unsorted(stage, M, L)) == 0) {
+            // every shard's block arrives sorted under R5 (the leg tails emit it so; ids grow with the local row): a
+            // candidate's merged rank is its own position plus, per other shard, the number of that shard's candidates
+            // ahead of it -- one binary search each, no exchange network (8 shards x top-100: 2048-wide bitonic = 66
+            // barrier-separated stages over 16-byte records against 8 x 8 probes per candidate)
+            int local = 0;
+            for (int i = threadIdx.x; i < M; i += blockDim.x) {
+                const b200rag_cand e = stage[i];
+                if (!e.valid) continue;
+                ++local;
+                const int sh = i / L;
+                int rank = i - sh * L;
+                for (int b = 0; b < n_shards && rank < L; ++b) {
+                    if (b == sh) continue;
+                    const b200rag_cand* lst = stage + (size_t)b * L;
+                    int lo = 0, hi = L;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const b200rag_cand o = lst[mid];
+                        if (o.valid && cand_better(o, e)) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo;
                 }
                 if (rank < L) { leg_id[leg * L + rank] = e.id; leg_score[leg * L + rank] = e.score; }
             }

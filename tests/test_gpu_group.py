@@ -48,6 +48,7 @@ def test_group_search_equals_single_shard_and_oracle(gpu):
     qf, ip, tt, ww = c.queries(6)
     qb = normalize_bf16(qf)
     for mode, k, mids in (("dense", 10, None), ("sparse", 10, None), ("hybrid", 10, None), ("hybrid", 100, None),
+                          ("dense", 100, None), ("sparse", 100, None),
                           ("hybrid", 10, np.asarray([0, 1, -1, 0, 1, 0], np.int32)),
                           ("dense", 5, np.asarray([1, 1, 1, 1, 1, 1], np.int32))):
         a = one.search(mode, k, qb, ip, tt, ww, mask_ids=mids)

@@ -243,7 +243,8 @@ def test_two_shards_fuse_equals_one(gpu):
     qf, ip, tt, ww = c.queries(5)
     qb = normalize_bf16(qf)
     dev = torch.device("cuda", gpu)
-    for mode, k in (("dense", 10), ("sparse", 10), ("hybrid", 10)):
+    # top-10: gathered sets of <= 128 candidates are ranked by counting; top-100: merged by rank (sorted shard blocks)
+    for mode, k in (("dense", 10), ("sparse", 10), ("hybrid", 10), ("dense", 100), ("sparse", 100), ("hybrid", 100)):
         ids1, sc1, cnt1 = one.search(mode, k, qb, ip, tt, ww)
         q, keep = a.make_query(mode, k, qb, ip, tt, ww)
         nlegs, L = Shard.legs_len(q)
@@ -264,6 +265,19 @@ def test_two_shards_fuse_equals_one(gpu):
         assert np.array_equal(out_sc.cpu().numpy(), sc1)
         g = gathered.cpu().numpy().view(CAND_DTYPE)
         assert g["valid"].max() == 1
+        if k == 100:
+            # blocks that are NOT in leg order (a foreign caller): the kernel notices and sorts instead of merging
+            gen = torch.Generator(device="cpu").manual_seed(7)
+            shuffled = gathered.clone()
+            for r in range(2):
+                for leg in range(nlegs):
+                    for qq in range(5):
+                        perm = torch.randperm(L, generator=gen).to(dev)
+                        shuffled[r, leg, qq] = gathered[r, leg, qq][perm]
+            o2, s2, c2 = torch.empty_like(out_ids), torch.empty_like(out_sc), torch.empty_like(out_cnt)
+            a.fuse(shuffled, 2, o2, s2, c2)
+            a.sync()
+            assert torch.equal(o2, out_ids) and torch.equal(s2, out_sc) and torch.equal(c2, out_cnt)
     for sh in (one, a, b):
         sh.close()
 
