@@ -312,6 +312,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_CUDA(cudaEventRecord(s->ev_scan[par], st));
         }
         s->stream = sd;                                            // the launchers below enqueue on s->stream
+        s->tail_beside_scan = true;                                // (this search's scan, then the next one's)
         int rc = B200RAG_OK;
         if (want_sparse) {
             if (!sparse_live) {
@@ -346,6 +347,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             }
         }
         s->stream = st;
+        s->tail_beside_scan = false;
         s->legs_classic = false;
         return rc;
     }
@@ -440,6 +442,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
             B2_CUDA(cudaMemsetAsync(aux.gkey, 0, (size_t)B * 8, sst));
             B2_CUDA(cudaMemsetAsync(aux.gthr, 0x80, (size_t)B * 4, sst));   // thresholds: 0x80808080 < any score
             s->stream = sst;                                   // the launchers below enqueue on s->stream
+            s->tail_beside_scan = overlap && want_dense;       // (on the side stream, next to the dense scan's CTAs)
             int rc = launch_sparse_scan(s, B, Lc, s->ws.lists_c.as<uint64_t>(), aux.eps, aux.gthr, aux.gkey);
             if (s->fused_tail && leg_tail_fits(sp_lists, Lc)) {
                 if (rc == B200RAG_OK) rc = launch_leg_tail(s, true, B, sp_lists, Lc, L, s->ws.lists_c.as<uint64_t>(), 1e-12f, 2e-6f,
@@ -451,6 +454,7 @@ static int run_legs(Shard* s, b200rag_cand* cands, int32_t* ambiguous) {
                 if (rc == B200RAG_OK) rc = launch_finalize_leg(s, B, Lc, L, approx, s->ws.exact2.as<uint64_t>(), 1e-12f, 2e-6f, aux.eps, 0, 0.f, out, ambiguous);
             }
             s->stream = st;
+            s->tail_beside_scan = false;
             if (rc != B200RAG_OK) return rc;
         }
     }

@@ -159,6 +159,7 @@ struct Shard {
     bool q8 = false;              // b200rag_set_compression
     int64_t q8_rows = 0;          // rows quantised so far (== n_rows whenever q8 is on)
     int q8_slack = 236;           // extra candidates of the 8-bit scan: rows inside its error band, at least 3 L (knob B200RAG_Q8_SLACK)
+    bool tail_beside_scan = false; // transient (run_legs -> launch_leg_tail): the tail must co-reside with a dense scan
     bool q8_pipeline = true;      // 8-bit scan in the pipelined form too (knob B200RAG_Q8_PIPELINE=0: classic form)
     DevBuf row_ids;               // i64 [n_rows] global id of every local row, strictly increasing (R1, R5)
     int64_t last_id = INT64_MIN;  // largest id stored so far

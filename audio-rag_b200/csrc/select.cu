@@ -350,28 +350,39 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
     //  NT -- Lc = 256: thread t only ever sees rank t mod 256 -- the maxima would be stratified by rank, the threshold as
     //  weak as the lists' tails, and nearly every key would survive: 250 us of radix select instead of 60 us.  Rotating
     //  the lane assignment by 37 slots per round gives every thread a spread of ranks and keeps the loads coalesced.)
-    uint64_t tmax = 0;
+    // (More than 32 keys per warp to guarantee -- Lc = 768 on 16 warps: the rounds are dealt to C classes, every class
+    //  guarantees ceil(Lc / C) keys by the same argument, and the weakest class threshold covers Lc.)
     {
-        int j = 0;
-        for (int base = 0; base < total; base += NT, ++j) {   // (independent loads: the compiler batches them)
-            const int i = base + ((tid + 37 * j) & (NT - 1));
-            const uint64_t k = i < total ? src[i] : 0ull;
-            tmax = k > tmax ? k : tmax;
-        }
-    }
-    {
-        uint64_t v = tmax;
-#pragma unroll
-        for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
-                const bool keep_max = (((lane & j) == 0) == ((lane & k) == 0));
-                v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
-            }
         const int kk = (p.Lc + NW - 1) / NW;
-        const uint64_t kth = kk <= 32 ? __shfl_sync(0xffffffffu, v, kk - 1) : 0ull;
-        if (lane == 0) wk_s[warp] = kth;
+        const int C = (kk + 31) / 32;                      // 1 unless Lc > 32 * #warps
+        const int kc = (kk + C - 1) / C;                   // keys per warp and class, <= 32
+        uint64_t wmin = ~0ull;
+        for (int cl = 0; cl < C; ++cl) {
+            uint64_t tmax = 0;
+            int j = cl;
+            for (int base = cl * NT; base < total; base += 8 * C * NT, j += 8 * C) {   // eight independent loads in flight
+                uint64_t k8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * C * NT + ((tid + 37 * (j + u * C)) & (NT - 1));
+                    k8[u] = i < total ? src[i] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tmax = k8[u] > tmax ? k8[u] : tmax;
+            }
+            uint64_t v = tmax;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v, jj);
+                    const bool keep_max = (((lane & jj) == 0) == ((lane & k) == 0));
+                    v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+                }
+            const uint64_t kth = __shfl_sync(0xffffffffu, v, kc - 1);
+            wmin = kth < wmin ? kth : wmin;
+        }
+        if (lane == 0) wk_s[warp] = wmin;
     }
     __syncthreads();
     uint64_t tau = wk_s[0];
@@ -382,16 +393,16 @@ __global__ void __launch_bounds__(NT) leg_tail_kernel(const TailParams p) {
         tau = gk > tau ? gk : tau;
     }
     if (tau == 0) tau = 1;                 // fewer than Lc real keys: keep every non-empty slot
-    // survivors: four keys per thread and round in flight, one shared atomic per warp and key group (warp-uniform trips)
-    for (int i0 = warp * 128; i0 < total; i0 += NT * 4) {
-        uint64_t k4[4];
+    // survivors: eight keys per thread and round in flight, one shared atomic per warp and key group (warp-uniform trips)
+    for (int i0 = warp * 256; i0 < total; i0 += NT * 8) {
+        uint64_t k4[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * 32 + lane;
             k4[u] = i < total ? src[i] : 0ull;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const bool take = k4[u] >= tau;
             const unsigned m = __ballot_sync(0xffffffffu, take);
             if (m != 0) {
@@ -572,10 +583,11 @@ int launch_leg_tail(Shard* s, bool sparse, int batch, int n_lists, int Lc, int L
     }
     // More than 64 candidates per leg (top-k beyond ~20): more warps, so that the per-warp k-th-largest threshold works
     // (k = ceil(Lc / #warps) <= 32) and more candidates are re-scored at a time -- 32 warps when the tail runs alone,
-    // 16 in pipelined mode, where it must CO-RESIDE with the next search's dense scan (a 1024-thread CTA does not fit the
-    // register file beside a scan CTA: it would wait for the whole scan to drain and serialise the pipeline; measured at
-    // 12.5M rows, top-100: 4.9 ms per step instead of 4.1).
-    const bool beside_scan = s->pipeline && !s->pipeline_paused;
+    // 16 when it must CO-RESIDE with a dense scan (s->tail_beside_scan, set by run_legs: every tail of the pipelined form,
+    // and the sparse leg's tail whenever that leg overlaps the dense scan): a 1024-thread CTA does not fit the register
+    // file beside a scan CTA; it would wait for the whole scan to drain and run after it (measured at 12.5M rows,
+    // top-100: 4.9 ms per step instead of 4.1).
+    const bool beside_scan = s->tail_beside_scan;
     if (sparse && Lc > 64 && !beside_scan) leg_tail_kernel<true, 1024><<<batch, 1024, sparse_smem(32), s->stream>>>(p);
     else if (sparse && Lc > 64) leg_tail_kernel<true, 512><<<batch, 512, sparse_smem(16), s->stream>>>(p);
     else if (sparse) leg_tail_kernel<true, 256><<<batch, 256, sparse_smem(8), s->stream>>>(p);
@@ -614,7 +626,7 @@ __device__ __forceinline__ int block_unsorted(const b200rag_cand* stage, int M, 
     return bad;
 }
 
-// smem layout: stage[M] cands | leg_id[2][L] i64 | leg_n[2] | fused[2L] f64 | fid[2L] i64 | ford[2L] int
+// smem layout: stage[M] cands | leg_id[2][L] i64 | leg_score[2L] f32 | fused[2L] f64 | fid[2L] i64 | ford[2L] int | rnk[2L] int
 __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restrict__ gathered, int n_shards,
                                                    int64_t shard_stride, int has_trailer, int nlegs, int batch,
                                                    int L, int top_k, int rrf_k,
@@ -630,6 +642,7 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
     double* fused = reinterpret_cast<double*>(leg_score + 2 * L);
     int64_t* fid = reinterpret_cast<int64_t*>(fused + 2 * L);
     int* ford = reinterpret_cast<int*>(fid + 2 * L);
+    int* rnk = ford + 2 * L;
     __shared__ int leg_n[2];
     __shared__ int total_s;
     const int q = blockIdx.x;
@@ -788,22 +801,36 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const b200rag_cand* __restri
             fused[e] = dup ? -1.0 : 1.0 / (double)(rrf_k + j);
             fid[e] = id; ford[e] = dup ? -1 : e;
         }
+        rnk[e] = 0;
+    }
+    __syncthreads();
+    // rank by counting (fused score desc, then first-leg order), P threads per entry so that a wide CTA is busy
+    // (top-100: 400 entries on 1024 threads -- 200 compares per thread instead of 2 rounds of 400)
+    const int P = NE > 0 ? min(32, max(1, (int)blockDim.x / NE)) : 1;
+    for (int it = threadIdx.x; it < NE * P; it += blockDim.x) {
+        const int e = it / P, part = it - e * P;
+        const int oe = ford[e];
+        if (oe < 0) continue;
+        const int f0 = (int)((long long)NE * part / P), f1 = (int)((long long)NE * (part + 1) / P);
+        const double se = fused[e];
+        int c = 0;
+        for (int f = f0; f < f1; ++f) {
+            const int of = ford[f];
+            if (of < 0) continue;
+            const double sf = fused[f];
+            if (sf > se || (sf == se && of < oe)) ++c;
+        }
+        if (c) atomicAdd(&rnk[e], c);
     }
     __syncthreads();
     int local = 0;
     for (int e = threadIdx.x; e < NE; e += blockDim.x) {
         if (ford[e] < 0) continue;
         ++local;
-        const double se = fused[e];
-        int rank = 0;
-        for (int f = 0; f < NE; ++f) {
-            if (ford[f] < 0) continue;
-            const double sf = fused[f];
-            if (sf > se || (sf == se && ford[f] < ford[e])) ++rank;
-        }
+        const int rank = rnk[e];
         if (rank < top_k) {
             out_ids[(size_t)q * top_k + rank] = fid[e];
-            out_scores[(size_t)q * top_k + rank] = se;
+            out_scores[(size_t)q * top_k + rank] = fused[e];
         }
     }
     if (local) atomicAdd(&total_s, local);
@@ -852,7 +879,7 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
                 int64_t shard_stride_override, const unsigned long long* wait_flags, unsigned long long wait_epoch) {
     const int nlegs = mode == B200RAG_HYBRID ? 2 : 1;
     const size_t M = (size_t)next_pow2(n_shards * L);
-    const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4) + 64;
+    const size_t smem = M * sizeof(b200rag_cand) + (size_t)2 * L * (8 + 4 + 8 + 8 + 4 + 4) + 64;
     if (smem > 200 * 1024) { set_error("fuse: n_shards * L too large"); return B200RAG_ERR_INVALID; }
     static AttrCache attr, carve;
     if (smem > 48 * 1024 && attr.raise(s->cfg.device, smem))
@@ -861,9 +888,10 @@ int launch_fuse(Shard* s, int mode, int batch, int L, int top_k, int rrf_k, cons
         B2_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t shard_stride = shard_stride_override > 0 ? shard_stride_override
                                                            : (int64_t)nlegs * batch * L + (has_trailer ? 1 : 0);
-    // the bitonic merge of large sets wants more lanes; in pipelined mode the kernel must fit beside a dense-scan CTA
-    const bool beside_scan = s->pipeline && !s->pipeline_paused;
-    const int fuse_threads = (size_t)n_shards * L > 512 ? (beside_scan ? 512 : 1024) : 256;
+    // large sets (the merge over many shards, the rank-by-counting of 2L fused entries) want more lanes; after pipelined
+    // legs the kernel runs on the second stream and must fit beside the next search's dense-scan CTA
+    const bool beside_scan = s->pipeline && !s->pipeline_paused && !s->legs_classic;
+    const int fuse_threads = ((size_t)n_shards * L > 512 || L > 64) ? (beside_scan ? 512 : 1024) : 256;
     fuse_kernel<<<batch, fuse_threads, smem, s->stream>>>(gathered, n_shards, shard_stride, has_trailer, nlegs, batch, L, top_k,
                                                  rrf_k, out_ids, out_scores, out_counts, wait_flags, wait_epoch,
                                                  s->x_timeout_cycles);
