@@ -90,3 +90,29 @@ def test_q8_follows_compaction_and_reload(gpu, tmp_path):
     assert back.stats()["dense_path"] == 3 and all(np.array_equal(x, y) for x, y in zip(r1, r2))
     sh.close()
     back.close()
+
+
+def test_q8_guard_failure_retries_on_bf16(gpu):
+    """3 000 near-copies of one row, closer to each other than the 8-bit error band is wide: the 8-bit scan cannot
+    separate them (its weakest retained upper bound stays above the L-th exact score), says so, and the search is
+    answered by the bf16 scan (or, if that is ambiguous too, exhaustively) -- never by the unproven candidate set."""
+    from b200rag import Shard, normalize_bf16
+    c = Corpus(30_000, dim=1024, vocab=40_009)
+    rng = np.random.default_rng(5)
+    target = rng.standard_normal(1024).astype(np.float32)
+    target /= np.linalg.norm(target)
+    near = target[None, :] + rng.standard_normal((3000, 1024)).astype(np.float32) * (0.05 / 32.0)
+    c.bits[10_000:13_000] = normalize_bf16(near)
+    sh = Shard(dim=1024, vocab=c.vocab, device=gpu, docs_per_block=2048)
+    sh.add(c.bits, c.indptr, c.terms, c.w)
+    sh.set_compression(True)
+    qb = normalize_bf16(target[None, :])
+    qf, ip, tt, ww = c.queries(1)
+    for mode, k in (("dense", 10), ("hybrid", 10)):
+        st = _check(sh, c, mode, qb, ip, tt, ww, k, ctx="q8 near-copies")
+        assert st["retries"] > 0, "3 000 rows inside the error band fit no candidate list: the guard must have fired"
+    # an ordinary query right after: the 8-bit scan again, first attempt
+    qb2 = normalize_bf16(qf)
+    st = _check(sh, c, "dense", qb2, ip, tt, ww, 10, ctx="q8 after a retry")
+    assert st["dense_path"] == 3 and st["retries"] == 0
+    sh.close()
