@@ -165,7 +165,7 @@ class B200Retriever(BaseRetriever):
     def __init__(self, config: RetrievalConfig, embedding_dim: int = 1024, *, device: int = 0,
                  devices: list[int] | str | None = None, vocab: int = 250_002, docs_per_block: int = 0,
                  rrf_k: int = 2, row_base: int = 0, compact_dead_fraction: float = 0.25,
-                 device_add_rows: int = 1024):
+                 device_add_rows: int = 1024, compressed_scan: bool | None = None):
         self.config = config
         self.embedding_dim = embedding_dim
         self._vocab, self._R, self._rrf_k, self._row_base = vocab, docs_per_block, rrf_k, row_base
@@ -174,6 +174,10 @@ class B200Retriever(BaseRetriever):
         self._devices_spec = devices if devices is not None else [device]
         self._compact_dead_fraction = float(compact_dead_fraction)
         self._device_add_rows = int(device_add_rows)
+        # opt-in 8-bit candidate scan (b200rag_set_compression): same results, half the bytes per search, +50 % HBM
+        if compressed_scan is None:
+            compressed_scan = os.environ.get("B200RAG_COMPRESSED_SCAN", "0") not in ("", "0")
+        self._compressed_scan = bool(compressed_scan)
         self._shards: list | None = None
         self._group = None
         self._existing_collections: set[str] = set()
@@ -235,6 +239,14 @@ class B200Retriever(BaseRetriever):
 
     def _set_shards(self, shards, group=None):
         self._shards = list(shards)
+        if getattr(self, "_compressed_scan", False):
+            for sh in self._shards:
+                if hasattr(sh, "set_compression"):
+                    try:
+                        sh.set_compression(True)
+                    except Exception as e:      # (e.g. an embedding width the 8-bit scan does not cover: same results without it)
+                        logger.warning(f"compressed candidate scan not available, continuing with the bf16 scan: {e}")
+                        break
         while len(self._shard_rows) < len(self._shards):
             self._shard_rows.append(_Grow(np.int64))
         if group is None and len(self._shards) > 1:

@@ -124,3 +124,31 @@ def test_save_load_round_trip(gpu, tmp_path):
     assert r3.count("fresh") == 40 and len(r3.search(qs[0], collection_name="fresh", search_type="hybrid")) == 6
     for x in (r, r2, r3):
         x.close()
+
+
+def test_compressed_scan_option_changes_nothing_but_the_scan(gpu):
+    """B200Retriever(compressed_scan=True) (or B200RAG_COMPRESSED_SCAN=1): the opt-in 8-bit candidate scan behind the
+    plugin -- same hits, same scores, and the engine says it took the 8-bit scan."""
+    if DIM not in (512, 1024):
+        pytest.skip("the 8-bit scan covers 512- and 1024-wide rows")
+    A, E, S = _types()
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever
+    try:
+        conf = RetrievalConfig(qdrant_in_memory=True, top_k=6)
+    except TypeError:
+        conf = RetrievalConfig(top_k=6)
+    plain = B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024)
+    comp = B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024, compressed_scan=True)
+    ch, em = make_chunks(900, 61, "C", A, E, S)
+    for s in range(0, 900, 300):
+        plain.add(ch[s:s + 300], em[s:s + 300], "c1")
+        comp.add(ch[s:s + 300], em[s:s + 300], "c1")
+    for q in make_queries(4, 62, 900, 61, E, S):
+        for st in ("dense", "hybrid"):
+            a = result_rows(plain.search(q, collection_name="c1", search_type=st))
+            b = result_rows(comp.search(q, collection_name="c1", search_type=st))
+            assert a == b and len(a) > 0
+            assert comp._shard.stats()["dense_path"] == 3 and plain._shard.stats()["dense_path"] == 1
+    plain.close()
+    comp.close()
