@@ -9,8 +9,8 @@ DIM = 256
 VOCAB = 250_002
 
 
-def make_chunks(n, seed, collection_tag, AudioChunk, EmbeddingResult, SparseVector, sparse=True, row_start=0):
-    dense = synth.dense_rows_f32(seed, row_start, n, DIM)
+def make_chunks(n, seed, collection_tag, AudioChunk, EmbeddingResult, SparseVector, sparse=True, row_start=0, dim=DIM):
+    dense = synth.dense_rows_f32(seed, row_start, n, dim)
     thr = synth.zipf_thresholds(VOCAB)
     ip, tt, ww = synth.sparse_docs_csr(seed, row_start, n, 10_000, VOCAB, 64, thr, synth.bm25_tables(10_000, VOCAB, 64))
     chunks, embs = [], []
@@ -29,8 +29,8 @@ def make_chunks(n, seed, collection_tag, AudioChunk, EmbeddingResult, SparseVect
     return chunks, embs
 
 
-def make_queries(nq, seed, n_rows, corpus_seed, EmbeddingResult, SparseVector, sparse=True):
-    qf = synth.dense_queries_f32(seed, 0, nq, n_rows, DIM, corpus_seed=corpus_seed)
+def make_queries(nq, seed, n_rows, corpus_seed, EmbeddingResult, SparseVector, sparse=True, dim=DIM):
+    qf = synth.dense_queries_f32(seed, 0, nq, n_rows, dim, corpus_seed=corpus_seed)
     qi, qt, qw = synth.sparse_queries(seed, 0, nq, 10, VOCAB)
     out = []
     for i in range(nq):

@@ -128,9 +128,7 @@ def test_save_load_round_trip(gpu, tmp_path):
 
 def test_compressed_scan_option_changes_nothing_but_the_scan(gpu):
     """B200Retriever(compressed_scan=True) (or B200RAG_COMPRESSED_SCAN=1): the opt-in 8-bit candidate scan behind the
-    plugin -- same hits, same scores, and the engine says it took the 8-bit scan."""
-    if DIM not in (512, 1024):
-        pytest.skip("the 8-bit scan covers 512- and 1024-wide rows")
+    plugin -- same hits, same scores, and the engine says it took the 8-bit scan (1024-wide rows, BGE-M3's width)."""
     A, E, S = _types()
     from b200rag.compat import RetrievalConfig
     from b200rag.retriever import B200Retriever
@@ -138,17 +136,23 @@ def test_compressed_scan_option_changes_nothing_but_the_scan(gpu):
         conf = RetrievalConfig(qdrant_in_memory=True, top_k=6)
     except TypeError:
         conf = RetrievalConfig(top_k=6)
-    plain = B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024)
-    comp = B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024, compressed_scan=True)
-    ch, em = make_chunks(900, 61, "C", A, E, S)
+    plain = B200Retriever(conf, embedding_dim=1024, device=gpu, docs_per_block=1024)
+    comp = B200Retriever(conf, embedding_dim=1024, device=gpu, docs_per_block=1024, compressed_scan=True)
+    ch, em = make_chunks(900, 61, "C", A, E, S, dim=1024)
     for s in range(0, 900, 300):
         plain.add(ch[s:s + 300], em[s:s + 300], "c1")
         comp.add(ch[s:s + 300], em[s:s + 300], "c1")
-    for q in make_queries(4, 62, 900, 61, E, S):
+    for q in make_queries(4, 62, 900, 61, E, S, dim=1024):
         for st in ("dense", "hybrid"):
             a = result_rows(plain.search(q, collection_name="c1", search_type=st))
             b = result_rows(comp.search(q, collection_name="c1", search_type=st))
             assert a == b and len(a) > 0
             assert comp._shard.stats()["dense_path"] == 3 and plain._shard.stats()["dense_path"] == 1
+    # a width the 8-bit scan does not cover: the option is dropped with a warning, the retriever works
+    small = B200Retriever(conf, embedding_dim=DIM, device=gpu, docs_per_block=1024, compressed_scan=True)
+    ch2, em2 = make_chunks(200, 63, "D", A, E, S)
+    small.add(ch2, em2, "c2")
+    assert len(small.search(make_queries(1, 64, 200, 63, E, S)[0], collection_name="c2", search_type="hybrid")) > 0
     plain.close()
     comp.close()
+    small.close()
