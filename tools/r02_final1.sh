@@ -13,4 +13,5 @@ import json,glob
 for f in ("gpurun_out/${T}_bench_driver_args.json","gpurun_out/${T}_bench_default.json"):
     d=json.load(open(f))
     print(f.split("/")[-1], round(d["value"],1), round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"],1), "plugin", round(d["e2e_plugin"]["value"],1), d["e2e_plugin"].get("matches_c_abi_path"), "oracle", d["oracle_check"].get("mismatches"), "frac", round(d["roofline"]["frac"],3), "incl", round(d["value_incl_copies"]["value"],1), d["clocks"], d["gpu_launches"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["measured_10k"]["ms_per_query"])
+    print("   compressed leg:", {k:v for k,v in (d.get("compressed_candidate_scan") or {}).items() if k!="note"})
 PY
