@@ -44,6 +44,12 @@ class OracleShard:
         self.ids = self.ids[keep]
         self.masks.clear()
 
+    def set_compression(self, on=True):
+        # the 8-bit candidate scan changes where candidates come from, never the result: nothing to model, only to record
+        if on and self.dim not in (512, 1024):
+            raise RuntimeError("set_compression: the 8-bit scan needs dim 512 or 1024")
+        self.calls.append(("set_compression", bool(on)))
+
     def clear(self):
         self.index = oracle.OracleIndex(self.dim)
         self.ids = np.zeros(0, dtype=np.int64)

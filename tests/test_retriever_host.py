@@ -329,3 +329,35 @@ def test_golden_fixture_is_current():
     path = os.path.join(os.path.dirname(__file__), "golden", "retrieval_golden.json")
     assert os.path.exists(path), "run python tests/golden/make_golden.py"
     assert json.load(open(path)) == json.loads(json.dumps(make_golden.generate()))
+
+
+def test_compressed_scan_option_reaches_every_shard(monkeypatch):
+    """compressed_scan=True / B200RAG_COMPRESSED_SCAN=1 -> set_compression(True) on each shard when the shards are set;
+    an engine that refuses (row width the 8-bit scan does not cover) costs a warning, not the retriever."""
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever
+    try:
+        conf = RetrievalConfig(qdrant_in_memory=True)
+    except TypeError:
+        conf = RetrievalConfig()
+    r = B200Retriever(conf, embedding_dim=1024, compressed_scan=True)
+    shards = [OracleShard(dim=1024), OracleShard(dim=1024)]
+    r._set_shards(shards, group=object())
+    assert all(("set_compression", True) in sh.calls for sh in shards)
+    monkeypatch.setenv("B200RAG_COMPRESSED_SCAN", "1")
+    r2 = B200Retriever(conf, embedding_dim=1024)
+    one = OracleShard(dim=1024)
+    r2._shard = one
+    assert ("set_compression", True) in one.calls
+    monkeypatch.setenv("B200RAG_COMPRESSED_SCAN", "0")
+    r3 = B200Retriever(conf, embedding_dim=1024)
+    off = OracleShard(dim=1024)
+    r3._shard = off
+    assert off.calls == []
+    r4 = B200Retriever(conf, embedding_dim=DIM, compressed_scan=True)      # 256-wide rows: refused by the engine
+    narrow = OracleShard(dim=DIM)
+    r4._shard = narrow
+    A, E, S = _types()
+    ch, em = make_chunks(20, 5, "N", A, E, S)
+    r4.add(ch, em, "n")
+    assert len(r4.search(make_queries(1, 6, 20, 5, E, S)[0], collection_name="n")) > 0
