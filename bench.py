@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000)
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-dense-1m", action="store_true",
+                    help="skip the CPU port's measured 1M-row dense-only figure (config 2 context, ~10 s)")
     ap.add_argument("--no-oracle-check", action="store_true", help="skip the full-corpus oracle check (profiling runs)")
     ap.add_argument("--no-compressed-leg", action="store_true",
                     help="skip the extra (non-headline) measurement of the opt-in 8-bit candidate scan")
@@ -168,8 +170,27 @@ def cpu_reference(a, steps, warmup, sample_rows):
                         "queries_per_s": float(1.0 / np.mean(t10)), "scaled": False}
     except Exception:
         pass
+    measured_dense_1m = None
+    if not a.no_cpu_dense_1m:
+        try:  # SURVEY 8d "Tier B at 1 M dense-only for config 2 context": fp32 sgemv + argsort over 1M x 1024 rows, MEASURED
+            n2 = 1_000_000
+            d2 = synth.bf16_bits_to_f32(fast.synth_dense_bf16(SEED, 0, n2, a.dim))
+            ref2 = oracle.RefShapedIndex(d2, np.zeros(n2 + 1, np.int64), np.zeros(0, np.uint32), np.zeros(0, np.float32))
+            q2 = synth.dense_queries_f32(QSEED, 0, 8, n2, a.dim, corpus_seed=SEED)
+            t2 = []
+            for i in range(8):
+                t0 = time.perf_counter()
+                ref2.dense_leg(q2[i], None, 10)
+                if i >= 2:
+                    t2.append(time.perf_counter() - t0)
+            measured_dense_1m = {"rows": n2, "top_k": 10, "search_type": "dense", "queries": len(t2),
+                                 "ms_per_query": float(np.mean(t2) * 1e3), "queries_per_s": float(1.0 / np.mean(t2)),
+                                 "scaled": False, "blas_threads": int(blas_threads)}
+            del d2, ref2
+        except Exception:
+            measured_dense_1m = None
     detail = {"value": qps, "unit": "queries/s", "cores": int(blas_threads), "kind": "port",
-              "measured_10k": measured_10k, "measured_ms_per_query_on_sample": per_query_sample * 1e3,
+              "measured_10k": measured_10k, "measured_dense_1m": measured_dense_1m, "measured_ms_per_query_on_sample": per_query_sample * 1e3,
               "sample_rows": n, "extrapolation_factor": scale,
               "sample": f"{len(times)} single hybrid queries over a {n}-row slice of the corpus "
                         f"({per_query_sample * 1e3:.1f} ms/query on the slice; BLAS sgemv uses {blas_threads} threads, "
