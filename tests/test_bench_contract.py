@@ -26,6 +26,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] * cbl["extrapolation_factor"] / 1e3 - 1.0) < 1e-9
     assert cbl["sample_rows"] == 1500 and abs(cbl["extrapolation_factor"] - 10_000_000 / 1500) < 1e-6
     assert cbl["measured_10k"]["scaled"] is False and cbl["measured_10k"]["queries_per_s"] > 0
+    assert cbl["measured_dense_1m"]["scaled"] is False and cbl["measured_dense_1m"]["rows"] == 1_000_000   # config 2 context
     assert d["steps"] * d["ms_per_step"] / 1e3 < 60, "the timed region must fit inside the run"
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
