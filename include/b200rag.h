@@ -226,7 +226,9 @@ int b200rag_fuse(b200rag_shard* s, const void* gathered_dev, int32_t n_shards, i
                  int64_t* out_ids_dev, double* out_scores_dev, int32_t* out_counts_dev);
 
 /* ---- persistence (the reference relies on Qdrant's volume, docker-compose.yml:36-37) -------------------------------
- * One file per shard: header | dense bf16 rows | forward sparse index (indptr, terms, weights).  The inverted index,
+ * One file per shard: header | dense bf16 rows | forward sparse index (indptr, terms, weights) | global row ids -- raw,
+ * contiguous arrays at offsets the 40-byte header determines, i.e. mmap-able; b200rag/shardfile.py documents the layout
+ * byte by byte and reads (numpy.memmap) and writes it without a GPU.  The inverted index,
  * directories and the weight bound are rebuilt on load (~0.2 s per 10M rows) so the file has no layout the kernels
  * depend on.  `load` needs an EMPTY shard created with the same dim and vocab; masks and payloads are the plugin's
  * (B200Retriever.save/load write them next to this file).  Returns B200RAG_ERR_INVALID on a foreign, mismatching
