@@ -1,5 +1,5 @@
 """b200rag/shardfile.py on the CPU: the documented layout of the engine's shard file, written and mapped back without a
-GPU (the engine-written file is compared with it in tests/test_gpu_exact.py::test_shard_file_is_the_documented_layout)."""
+GPU (the engine-written file is compared with it in tests/test_gpu_shardfile.py::test_shard_file_is_the_documented_layout)."""
 import os
 import struct
 
