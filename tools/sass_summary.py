@@ -6,7 +6,8 @@ the in-tree libb200rag.so; no GPU needed).  Writes profiles/<tag>_sass_summary.t
 
 UTCHMMA = tcgen05.mma (.2CTA: cta_group::2), UTMALDG = cp.async.bulk.tensor (TMA tile loads), UBLKCP = cp.async.bulk
 (1-D bulk copies), LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit, SYNCS = mbarrier operations,
-ATOMS.ADD = native shared-memory integer atomics, LDG.E.256 = 256-bit global loads."""
+ATOMS.ADD = native shared-memory integer atomics, IDP.2A = dp2a (16-bit x 8-bit integer dot-product steps of the 8-bit
+candidate scan), LDG.E.256 = 256-bit global loads."""
 import collections
 import os
 import re
@@ -16,7 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "audio-rag_b200", "b200rag", "libb200rag.so")
 WATCH = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "ATOMS.ADD", "ATOMS.CAST", "ATOMS.MAX",
-         "ATOMG", "RED", "LDG.E.256", "LDG.E.128", "LDS.128", "STS.128", "FFMA", "DFMA", "DADD", "DMUL", "SHFL", "BAR.SYNC",
+         "ATOMG", "RED", "IDP.2A", "LDG.E.256", "LDG.E.128", "LDS.128", "STS.128", "FFMA", "DFMA", "DADD", "DMUL", "SHFL", "BAR.SYNC",
          "MEMBAR", "CCTL", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS"]
 
 
