@@ -108,11 +108,13 @@ int b200rag_set_slack(b200rag_shard* s, int32_t slack);      /* extra approximat
  *                          (default 1; the environment variable B200RAG_EXACT_FALLBACK=0 sets the default to 0). */
 int b200rag_set_exhaustive(b200rag_shard* s, int32_t on);
 /* Corpus compression for the candidate scan (opt-in, dim 512 or 1024).  The shard keeps an 8-bit copy
- * of its rows ([n][dim + 16]: symmetric int8 per row + scale) beside the bf16 rows; searches of 1-2 queries scan THAT
- * (half the bytes), ranking rows by a rigorous UPPER BOUND of their exact score, keep a wider candidate set (the rows
- * inside the quantisation error band: `B200RAG_Q8_SLACK`, default 364 extra candidates) and re-score the candidates
- * exactly from the bf16 rows -- ids and scores stay bit-identical to the uncompressed path; when the guard does not clear,
- * the retry scans the bf16 rows.  Costs (dim + 16) bytes per row of HBM.  Maintained through add / compact / load. */
+ * of its rows ([n][dim + 16]: symmetric int8 per row + {scale, l1, residual norm}) beside the bf16 rows; searches of 1-2
+ * queries scan THAT (half the bytes), ranking rows by a rigorous UPPER BOUND of their exact score, keep a wider candidate
+ * set (the rows inside the quantisation error band: max(`B200RAG_Q8_SLACK` = 236, 3 L) extra candidates) and re-score the
+ * candidates exactly from the bf16 rows -- ids and scores stay bit-identical to the uncompressed path; when the guard does
+ * not clear, the retry scans the bf16 rows.  Costs (dim + 16) bytes per row of HBM.  Maintained through add / compact /
+ * load.  No reference counterpart (the reference's collections are created without quantisation, qdrant.py:95-118;
+ * Qdrant's own scalar quantisation with rescoring is approximate, this is not). */
 int b200rag_set_compression(b200rag_shard* s, int32_t on);
 int b200rag_set_exact_fallback(b200rag_shard* s, int32_t on);
 /* Pipelined searches (throughput mode for callers that enqueue search after search on staged batches: b200rag_legs ->
