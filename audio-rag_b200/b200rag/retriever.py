@@ -56,6 +56,29 @@ _PAYLOAD_CHUNK = 65536          # payloads per file in save()
 
 def _sorted_sparse(sv, vocab):
     """indices/values lists -> (uint32 ascending, float32); duplicates and out-of-range indices are rejected (R3)."""
+    ind, vals = sv.indices, sv.values
+    if isinstance(ind, list) and isinstance(vals, list) and len(ind) <= 64:
+        # a query's handful of terms (5-30 typical, SURVEY 8a): plain Python beats six numpy calls on a dozen items
+        n = len(ind)
+        if n != len(vals):
+            raise RetrievalError(f"sparse vector has {n} indices but {len(vals)} values")
+        if n == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.float32)
+        try:
+            pairs = sorted(zip(ind, vals))
+            lo, hi = pairs[0][0], pairs[-1][0]
+            if type(lo) is not int or type(hi) is not int:
+                raise TypeError
+        except TypeError:
+            pairs = None                                  # odd element types: let numpy decide, as before
+        if pairs is not None:
+            if lo < 0 or hi >= vocab:
+                raise RetrievalError(f"sparse index out of range [0, {vocab})")
+            idx = [p[0] for p in pairs]
+            for a, b in zip(idx, idx[1:]):
+                if a == b:
+                    raise RetrievalError("duplicate index in sparse vector")
+            return np.array(idx, dtype=np.uint32), np.array([p[1] for p in pairs], dtype=np.float32)
     idx = np.asarray(sv.indices, dtype=np.int64).reshape(-1)
     val = np.asarray(sv.values, dtype=np.float32).reshape(-1)
     if idx.shape != val.shape:
@@ -130,11 +153,14 @@ class _PayloadStore:
         return self._lazy_n + len(self._items)
 
     def __getitem__(self, i):
-        if i < 0 or i >= len(self):
+        j = i - self._lazy_n
+        if j >= 0:                                  # (the per-hit lookup of every search: no len() calls)
+            if j >= len(self._items):
+                raise IndexError(i)
+            return self._items[j]
+        if i < 0:
             raise IndexError(i)
-        if i < self._lazy_n:
-            return self._lazy_fn(int(i))
-        return self._items[i - self._lazy_n]
+        return self._lazy_fn(int(i))
 
     def __iter__(self):
         for i in range(len(self)):
@@ -500,13 +526,20 @@ class B200Retriever(BaseRetriever):
                 "score_threshold": threshold, "filter": dict(filter_metadata) if filter_metadata else None}
 
     def _materialise(self, ids, scores, count, resolved) -> list[RetrievalResult]:
+        n = int(count)
+        if n == 0:
+            return []
         out = []
-        for j in range(int(count)):
-            payload = self._payloads[int(ids[j]) - self._row_base]
-            chunk = AudioChunk(text=payload.get("text", ""), start=payload.get("start", 0.0),
-                               end=payload.get("end", 0.0), speaker=payload.get("speaker"),
-                               metadata=dict(payload["metadata"]) if payload.get("metadata") is not None else None)
-            out.append(RetrievalResult(chunk=chunk, score=float(scores[j]), source=resolved))
+        payloads, base = self._payloads, self._row_base
+        # (one tolist() per array instead of a numpy scalar + int()/float() per hit)
+        for rid, sc in zip(np.asarray(ids[:n]).tolist(), np.asarray(scores[:n], dtype=np.float64).tolist()):
+            payload = payloads[rid - base]
+            get = payload.get
+            md = get("metadata")
+            out.append(RetrievalResult(chunk=AudioChunk(text=get("text", ""), start=get("start", 0.0), end=get("end", 0.0),
+                                                        speaker=get("speaker"),
+                                                        metadata=dict(md) if md is not None else None),
+                                       score=sc, source=resolved))
         return out
 
     def _query_arrays(self, embeddings, mode):
@@ -524,6 +557,9 @@ class B200Retriever(BaseRetriever):
         q_bits = _ffi.normalize_bf16(dense)
         if mode == "dense":
             return q_bits, None, None, None
+        if len(embeddings) == 1:                    # the reference's single-query call: nothing to concatenate
+            t, w = _sorted_sparse(embeddings[0].sparse, self._vocab)
+            return q_bits, np.array([0, len(t)], dtype=np.int64), t, w
         indptr = np.zeros(len(embeddings) + 1, dtype=np.int64)
         tt, ww = [], []
         for i, e in enumerate(embeddings):
