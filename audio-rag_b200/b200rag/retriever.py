@@ -25,7 +25,7 @@ Additive API (no reference counterpart): ``search_batch``, ``search_batch_arrays
 """
 from __future__ import annotations
 
-import array
+import struct
 import json
 import os
 from collections import OrderedDict
@@ -204,6 +204,7 @@ class B200Retriever(BaseRetriever):
         if compressed_scan is None:
             compressed_scan = os.environ.get("B200RAG_COMPRESSED_SCAN", "0") not in ("", "0")
         self._compressed_scan = bool(compressed_scan)
+        self._pack_dense = None                 # struct.Struct("<dim>f"), built on first use
         self._shards: list | None = None
         self._group = None
         self._existing_collections: set[str] = set()
@@ -544,11 +545,14 @@ class B200Retriever(BaseRetriever):
 
     def _query_arrays(self, embeddings, mode):
         if len(embeddings) == 1 and isinstance(embeddings[0].dense, list):
-            # the single-query call of the reference (a Python list of floats): array('f') converts it twice as fast as
-            # numpy does (16 vs 32 us for 1024 floats) with the same double -> float rounding
+            # the single-query call of the reference (a Python list of floats): struct.pack converts it 2.6x as fast as
+            # numpy does (16 vs 41 us for 1024 floats; array('f'): 27 us) with the same double -> float rounding
             try:
-                dense = np.frombuffer(array.array("f", embeddings[0].dense), dtype=np.float32).reshape(1, -1)
-            except (TypeError, OverflowError):
+                pk = self._pack_dense
+                if pk is None:
+                    pk = self._pack_dense = struct.Struct(f"{self.embedding_dim}f")
+                dense = np.frombuffer(pk.pack(*embeddings[0].dense), dtype=np.float32).reshape(1, -1)
+            except (struct.error, TypeError, OverflowError):
                 dense = np.asarray([embeddings[0].dense], dtype=np.float32)
         else:
             dense = np.asarray([e.dense for e in embeddings], dtype=np.float32)

@@ -361,3 +361,46 @@ def test_compressed_scan_option_reaches_every_shard(monkeypatch):
     ch, em = make_chunks(20, 5, "N", A, E, S)
     r4.add(ch, em, "n")
     assert len(r4.search(make_queries(1, 6, 20, 5, E, S)[0], collection_name="n")) > 0
+
+
+def test_query_conversion_fast_paths_equal_numpy(built_lib):
+    """The single-query fast paths (struct.pack for the dense list, plain-Python sort for a short sparse vector) must hand
+    the engine exactly what the general numpy path builds -- same bf16 bits, same sorted terms and weights -- and must
+    reject what it rejects."""
+    import types
+    from audio_rag.core import RetrievalError
+    from b200rag import _ffi
+    from b200rag.compat import RetrievalConfig
+    from b200rag.retriever import B200Retriever, _sorted_sparse
+    A, E, S = _types()
+    r = B200Retriever(RetrievalConfig(qdrant_in_memory=True), embedding_dim=DIM)
+    rng = np.random.default_rng(9)
+    for trial in range(20):
+        dense64 = (rng.standard_normal(DIM) * 10.0 ** rng.integers(-6, 4)).tolist()       # Python doubles, as an embedder's .tolist()
+        if trial == 3:
+            dense64 = [int(x) for x in rng.integers(-5, 6, DIM)]                            # ints are numbers too
+        if trial == 4:
+            dense64 = list(np.asarray(dense64, np.float32))                                 # numpy scalars in a list
+        nt = int(rng.integers(0, 30))
+        idx = rng.choice(250_002, nt, replace=False).tolist()
+        val = rng.random(nt).tolist()
+        e = E(dense=dense64, sparse=S(indices=idx, values=val))
+        q_bits, ip, tt, ww = r._query_arrays([e], "hybrid")
+        assert np.array_equal(q_bits, _ffi.normalize_bf16(np.asarray([dense64], dtype=np.float32)))
+        o = np.argsort(np.asarray(idx, np.int64), kind="stable")
+        assert ip.tolist() == [0, nt] and tt.dtype == np.uint32 and ww.dtype == np.float32
+        assert np.array_equal(tt, np.asarray(idx, np.uint32)[o]) and np.array_equal(ww, np.asarray(val, np.float32)[o])
+        # ... and the batch path (numpy all the way) agrees with itself on the same query
+        qb2, ip2, tt2, ww2 = r._query_arrays([e, e], "hybrid")
+        assert np.array_equal(qb2[0], q_bits[0]) and np.array_equal(tt2[:nt], tt) and np.array_equal(ww2[:nt], ww)
+    long_idx = rng.choice(250_002, 200, replace=False).tolist()                             # > 64 terms: numpy path
+    t_long, _ = _sorted_sparse(S(indices=long_idx, values=[1.0] * 200), 250_002)
+    assert np.array_equal(t_long, np.sort(np.asarray(long_idx, np.uint32)))
+    for bad in (S(indices=[5, 5], values=[1.0, 2.0]), S(indices=[-1], values=[1.0]), S(indices=[250_002], values=[1.0]),
+                S(indices=[1, 2], values=[1.0])):
+        with pytest.raises(RetrievalError):
+            _sorted_sparse(bad, 250_002)
+    with pytest.raises(RetrievalError):
+        r._query_arrays([E(dense=[0.5] * (DIM - 1), sparse=None)], "dense")                 # wrong width
+    with pytest.raises(Exception):
+        r._query_arrays([E(dense=["x"] * DIM, sparse=None)], "dense")                       # not numbers
